@@ -1,0 +1,457 @@
+// hdsdp_b200/csrc/capi.cu -- extern "C" boundary of libhdsdp_cuda.so (declared in include/hdsdpcu.h).
+// Thin: argument checks, host<->device staging, and dispatch into chol.cu / cone.cu / kkt.cu.
+#include "../../include/hdsdpcu.h"
+#include "cone.h"
+#include <cstring>
+#include <vector>
+
+long g_hd_launches = 0;
+
+namespace {
+cudaStream_t g_stream = nullptr;
+bool g_ready = false;
+
+struct LinsysCU {
+    DenseChol *c;
+    double *d_vec;  // np x 8 staging for solves
+    double *d_inv;  // np x np, lazily
+};
+
+struct LpCU {
+    int m, ncol;
+    int *d_colptr, *d_rowidx;
+    double *d_val, *d_sinv;
+};
+
+int ensure_ready() {
+    if (g_ready) return HD_OK;
+    return hdsdpcu_init(-1);
+}
+} // namespace
+
+cudaStream_t hd_stream() { return g_stream; }
+
+extern "C" {
+
+int hdsdpcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hdsdpcu_init(int device) {
+    if (hdsdpcu_device_count() <= 0) {
+        fprintf(stderr, "[hdsdpcu] no CUDA device: the hot path has no CPU fallback\n");
+        return HD_FAILED;
+    }
+    if (device >= 0) HD_CUDA(cudaSetDevice(device));
+    if (!g_stream) HD_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_ready = true;
+    return HD_OK;
+}
+
+void *hdsdpcu_stream(void) { return (void *) g_stream; }
+int hdsdpcu_sync(void) {
+    if (!g_ready) return HD_FAILED;
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    return HD_OK;
+}
+const char *hdsdpcu_version(void) { return "hdsdp-b200 0.1 (sm_100a)"; }
+long hdsdpcu_launch_count(int reset) {
+    long v = g_hd_launches;
+    if (reset) g_hd_launches = 0;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// B1: dense linear system back-end
+// ------------------------------------------------------------------------------------------------
+int hdsdpcu_linsys_create(void **pchol, int nCol) {
+    if (!pchol) return HD_FAILED;
+    HD_CALL(ensure_ready());
+    LinsysCU *l = (LinsysCU *) calloc(1, sizeof(LinsysCU));
+    if (!l) return HD_MEMORY;
+    int rc = chol_create(&l->c, nCol);
+    if (rc != HD_OK) { free(l); return rc; }
+    if (cudaMalloc(&l->d_vec, sizeof(double) * (size_t) l->c->np * 8) != cudaSuccess) {
+        cudaGetLastError(); chol_destroy(l->c); free(l); return HD_MEMORY;
+    }
+    *pchol = l;
+    return HD_OK;
+}
+
+void hdsdpcu_linsys_setparam(void *chol, void *param) { (void) chol; (void) param; }
+int hdsdpcu_linsys_symbolic(void *chol, int *colBeg, int *colIdx) { (void) chol; (void) colBeg; (void) colIdx; return HD_OK; }
+
+static int linsys_load_host(LinsysCU *l, const double *elem) {
+    DenseChol *c = l->c;
+    HD_CUDA(cudaMemcpy2DAsync(c->L, (size_t) c->np * 8, elem, (size_t) c->n * 8, (size_t) c->n * 8, c->n,
+                              cudaMemcpyHostToDevice, g_stream));
+    HD_CALL(hd_pad_identity(g_stream, c->L, c->np, c->n, c->np));
+    c->factored = false;
+    return HD_OK;
+}
+
+int hdsdpcu_linsys_numeric(void *chol, int *colBeg, int *colIdx, double *elem) {
+    (void) colBeg; (void) colIdx;
+    LinsysCU *l = (LinsysCU *) chol;
+    HD_CALL(linsys_load_host(l, elem));
+    int info = 0;
+    HD_CALL(chol_factor(g_stream, l->c, &info));
+    return info == 0 ? HD_OK : HD_FAILED;
+}
+
+int hdsdpcu_linsys_psdcheck(void *chol, int *colBeg, int *colIdx, double *elem, int *isPsd) {
+    (void) colBeg; (void) colIdx;
+    LinsysCU *l = (LinsysCU *) chol;
+    HD_CALL(linsys_load_host(l, elem));
+    int info = 0;
+    HD_CALL(chol_factor(g_stream, l->c, &info));
+    *isPsd = (info == 0);
+    return HD_OK;
+}
+
+// mode 0: L \ rhs, 1: L' \ rhs, 2: both
+static int linsys_solve_host(LinsysCU *l, int nRhs, double *rhs, double *sol, int mode) {
+    DenseChol *c = l->c;
+    if (!c->factored) return HD_FAILED;
+    const int n = c->n, np = c->np;
+    double *out = sol ? sol : rhs;
+    for (int r0 = 0; r0 < nRhs; r0 += 8) {
+        int nb = (nRhs - r0 < 8) ? nRhs - r0 : 8;
+        HD_CUDA(cudaMemsetAsync(l->d_vec, 0, sizeof(double) * (size_t) np * nb, g_stream));
+        HD_CUDA(cudaMemcpy2DAsync(l->d_vec, (size_t) np * 8, rhs + (size_t) r0 * n, (size_t) n * 8, (size_t) n * 8, nb,
+                                  cudaMemcpyHostToDevice, g_stream));
+        if (mode == 0 || mode == 2) HD_CALL(chol_fsolve(g_stream, c, l->d_vec, nb, np));
+        if (mode == 1 || mode == 2) HD_CALL(chol_bsolve(g_stream, c, l->d_vec, nb, np));
+        HD_CUDA(cudaMemcpy2DAsync(out + (size_t) r0 * n, (size_t) n * 8, l->d_vec, (size_t) np * 8, (size_t) n * 8, nb,
+                                  cudaMemcpyDeviceToHost, g_stream));
+        HD_CUDA(cudaStreamSynchronize(g_stream));
+    }
+    return HD_OK;
+}
+
+void hdsdpcu_linsys_fsolve(void *chol, int nRhs, double *rhs, double *sol) { linsys_solve_host((LinsysCU *) chol, nRhs, rhs, sol, 0); }
+void hdsdpcu_linsys_bsolve(void *chol, int nRhs, double *rhs, double *sol) { linsys_solve_host((LinsysCU *) chol, nRhs, rhs, sol, 1); }
+int hdsdpcu_linsys_solve(void *chol, int nRhs, double *rhs, double *sol) { return linsys_solve_host((LinsysCU *) chol, nRhs, rhs, sol, 2); }
+
+int hdsdpcu_linsys_getdiag(void *chol, double *diag) {
+    LinsysCU *l = (LinsysCU *) chol;
+    DenseChol *c = l->c;
+    HD_CUDA(cudaMemcpy2DAsync(diag, 8, c->L, (size_t) (c->np + 1) * 8, 8, c->n, cudaMemcpyDeviceToHost, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    return HD_OK;
+}
+
+void hdsdpcu_linsys_invert(void *chol, double *fullInv, double *aux) {
+    (void) aux;
+    LinsysCU *l = (LinsysCU *) chol;
+    DenseChol *c = l->c;
+    if (!l->d_inv && cudaMalloc(&l->d_inv, sizeof(double) * (size_t) c->np * c->np) != cudaSuccess) {
+        fprintf(stderr, "[hdsdpcu] linsys_invert: out of device memory\n");
+        return;
+    }
+    if (chol_invert(g_stream, c, l->d_inv) != HD_OK) return;
+    HD_CUDA_VOID(cudaMemcpy2DAsync(fullInv, (size_t) c->n * 8, l->d_inv, (size_t) c->np * 8, (size_t) c->n * 8, c->n,
+                                   cudaMemcpyDeviceToHost, g_stream));
+    HD_CUDA_VOID(cudaStreamSynchronize(g_stream));
+}
+
+void hdsdpcu_linsys_destroy(void **pchol) {
+    if (!pchol || !*pchol) return;
+    LinsysCU *l = (LinsysCU *) *pchol;
+    chol_destroy(l->c);
+    if (l->d_vec) cudaFree(l->d_vec);
+    if (l->d_inv) cudaFree(l->d_inv);
+    free(l);
+    *pchol = nullptr;
+}
+
+int hdsdpcu_linsys_padded_dim(void *chol) { return ((LinsysCU *) chol)->c->np; }
+int hdsdpcu_linsys_numeric_dev(void *chol, const double *d_elem, long ld, int *info) {
+    LinsysCU *l = (LinsysCU *) chol;
+    HD_CALL(chol_load_dev(g_stream, l->c, d_elem, ld));
+    int inf = 0;
+    HD_CALL(chol_factor(g_stream, l->c, &inf));
+    if (info) *info = inf;
+    return HD_OK;
+}
+int hdsdpcu_linsys_solve_dev(void *chol, int nRhs, double *d_x, long ldx) {
+    LinsysCU *l = (LinsysCU *) chol;
+    if (!l->c->factored) return HD_FAILED;
+    HD_CALL(chol_fsolve(g_stream, l->c, d_x, nRhs, ldx));
+    return chol_bsolve(g_stream, l->c, d_x, nRhs, ldx);
+}
+int hdsdpcu_linsys_invert_dev(void *chol, double *d_inv) { return chol_invert(g_stream, ((LinsysCU *) chol)->c, d_inv); }
+double *hdsdpcu_linsys_factor_dev(void *chol) { return ((LinsysCU *) chol)->c->L; }
+
+// ------------------------------------------------------------------------------------------------
+// B2: cone
+// ------------------------------------------------------------------------------------------------
+int hdsdpcu_cone_create(void **pcone, int nRow, int nCol, const int *beg, const int *idx, const double *elem) {
+    if (!pcone) return HD_FAILED;
+    HD_CALL(ensure_ready());
+    ConeCU *c = nullptr;
+    int rc = cone_create(&c, nRow, nCol, beg, idx, elem);
+    if (rc != HD_OK) return rc;
+    *pcone = c;
+    return HD_OK;
+}
+void hdsdpcu_cone_destroy(void **pcone) {
+    if (!pcone || !*pcone) return;
+    cone_destroy((ConeCU *) *pcone);
+    *pcone = nullptr;
+}
+int hdsdpcu_cone_getdim(void *cone) { return ((ConeCU *) cone)->n; }
+int hdsdpcu_cone_gettypes(void *cone, int *types) {
+    ConeCU *c = (ConeCU *) cone;
+    for (int i = 0; i <= c->m; ++i) types[i] = c->types[i];
+    return HD_OK;
+}
+void hdsdpcu_cone_setstart(void *cone, double r) { ((ConeCU *) cone)->dualResidual = r; }
+void hdsdpcu_cone_reduceresi(void *cone, double r) { ((ConeCU *) cone)->dualResidual = r; }
+void hdsdpcu_cone_setperturb(void *cone, double p) { ((ConeCU *) cone)->dualPerturb = p; }
+
+int hdsdpcu_cone_update(void *cone, double tau, const double *y) {
+    ConeCU *c = (ConeCU *) cone;
+    return cone_update_buffer(c, tau, -1.0, y, nullptr, -c->dualResidual, BUF_DUALVAR); // hdsdp_conic_sdp.c:1630
+}
+int hdsdpcu_cone_update_dev(void *cone, double tau, const double *d_y) {
+    ConeCU *c = (ConeCU *) cone;
+    return cone_update_buffer(c, tau, -1.0, nullptr, d_y, -c->dualResidual, BUF_DUALVAR);
+}
+int hdsdpcu_cone_updatebuffer(void *cone, double cC, double aS, const double *a, double eye, int which) {
+    return cone_update_buffer((ConeCU *) cone, cC, aS, a, nullptr, eye, which);
+}
+int hdsdpcu_cone_factorize(void *cone, int which, int *isPsd) { return cone_factorize((ConeCU *) cone, which, isPsd); }
+int hdsdpcu_cone_interiorcheck(void *cone, double tau, const double *y, int *isInterior) {
+    HD_CALL(hdsdpcu_cone_update(cone, tau, y));
+    return cone_factorize((ConeCU *) cone, BUF_DUALVAR, isInterior);
+}
+int hdsdpcu_cone_interiorcheckexpert(void *cone, double cC, double aS, const double *a, double eye, int which, int *isInterior) {
+    HD_CALL(cone_update_buffer((ConeCU *) cone, cC, aS, a, nullptr, eye, which));
+    return cone_factorize((ConeCU *) cone, which == BUF_DUALVAR ? BUF_DUALVAR : BUF_DUALCHECK, isInterior);
+}
+int hdsdpcu_cone_getbarrier(void *cone, double tau, const double *y, int which, double *logdet) {
+    ConeCU *c = (ConeCU *) cone;
+    if (y) {
+        if (which != BUF_DUALVAR) return HD_FAILED;
+        HD_CALL(hdsdpcu_cone_update(cone, tau, y));
+        int psd = 0;
+        HD_CALL(cone_factorize(c, BUF_DUALVAR, &psd));
+        if (!psd) return HD_FAILED; // reference: HFpLinsysNumeric fails when dpotrf does
+    }
+    DenseChol *f = (which == BUF_DUALVAR) ? c->factor : c->checker;
+    HD_CALL(chol_logdet(g_stream, f, c->d_scal + 7, nullptr));
+    HD_CUDA(cudaMemcpyAsync(c->h_scal + 7, c->d_scal + 7, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    *logdet = c->h_scal[7];
+    return HD_OK;
+}
+}
+
+namespace {
+__global__ void axpy_full_kernel(double *dst, const double *src, long total, double alpha) {
+    long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) dst[idx] += alpha * src[idx];
+}
+__global__ void scal_kernel(double *x, long total, double a) {
+    long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) x[idx] *= a;
+}
+} // namespace
+
+extern "C" {
+
+int hdsdpcu_cone_addstepandcheck(void *cone, double dStep, int which, int *isInterior) {
+    // reference hdsdp_conic_sdp.c:2333-2360: (checker <- S if not DUALVAR); target += dStep * dS; PSD check
+    ConeCU *c = (ConeCU *) cone;
+    const long total = (long) c->np * c->np;
+    int tgt = (which == BUF_DUALVAR) ? BUF_DUALVAR : BUF_DUALCHECK;
+    if (tgt == BUF_DUALCHECK)
+        HD_CUDA(cudaMemcpyAsync(c->d_buf[BUF_DUALCHECK], c->d_buf[BUF_DUALVAR], sizeof(double) * total, cudaMemcpyDeviceToDevice, g_stream));
+    HDK(axpy_full_kernel)<<<(unsigned) ((total + 255) / 256), 256, 0, g_stream>>>(c->d_buf[tgt], c->d_buf[BUF_DUALSTEP], total, dStep);
+    HD_CUDA(cudaGetLastError());
+    return cone_factorize(c, tgt, isInterior);
+}
+
+int hdsdpcu_cone_scal(void *cone, double dScal) {
+    // sdpDataMatScal on the objective (hdsdp_conic_sdp.c:1604-1614): scale every representation of C
+    ConeCU *c = (ConeCU *) cone;
+    const int m = c->m;
+    HostCoeff &h = c->coeff[m];
+    for (double &v : h.val) v *= dScal;
+    for (double &v : h.packed) v *= dScal;
+    h.sign *= dScal;
+    // S-assembly lists: entries with con == m ; simplest is to rescale through a tiny kernel over all entries
+    // (done on the host copy and re-uploaded: objective scaling happens once per solve)
+    std::vector<int> con;
+    std::vector<double> val;
+    int nent = 0;
+    if (c->npos > 0) {
+        HD_CUDA(cudaMemcpy(&nent, c->d_pos_ptr + c->npos, sizeof(int), cudaMemcpyDeviceToHost));
+        con.resize(nent); val.resize(nent);
+        HD_CUDA(cudaMemcpy(con.data(), c->d_ent_con, sizeof(int) * nent, cudaMemcpyDeviceToHost));
+        HD_CUDA(cudaMemcpy(val.data(), c->d_ent_val, sizeof(double) * nent, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < nent; ++e) if (con[e] == m) val[e] *= dScal;
+        HD_CUDA(cudaMemcpy(c->d_ent_val, val.data(), sizeof(double) * nent, cudaMemcpyHostToDevice));
+    }
+    if (h.type == COEFF_DENSE) {
+        std::vector<int> dcon(c->nds);
+        HD_CUDA(cudaMemcpy(dcon.data(), c->d_dense_con, sizeof(int) * c->nds, cudaMemcpyDeviceToHost));
+        for (int d = 0; d < c->nds; ++d)
+            if (dcon[d] == m) HDK(scal_kernel)<<<(unsigned) ((c->npack + 255) / 256), 256, 0, g_stream>>>(c->d_dense_packed + (long) d * c->npack, c->npack, dScal);
+    }
+    if (h.type == COEFF_DSR1) {
+        std::vector<int> dcon(c->ndr1p);
+        HD_CUDA(cudaMemcpy(dcon.data(), c->d_dr1_con, sizeof(int) * c->ndr1p, cudaMemcpyDeviceToHost));
+        for (int d = 0; d < c->ndr1; ++d)
+            if (dcon[d] == m) HDK(scal_kernel)<<<1, 32, 0, g_stream>>>(c->d_dr1_sign + d, 1, dScal);
+    }
+    if (c->d_obj_val) HDK(scal_kernel)<<<(unsigned) ((c->obj_nent + 255) / 256), 256, 0, g_stream>>>(c->d_obj_val, c->obj_nent, dScal);
+    if (c->d_obj_full) {
+        long total = (long) c->np * c->np;
+        HDK(scal_kernel)<<<(unsigned) ((total + 255) / 256), 256, 0, g_stream>>>(c->d_obj_full, total, dScal);
+    }
+    HD_CUDA(cudaGetLastError());
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    return HD_OK;
+}
+
+int hdsdpcu_cone_buildschur(void *cone, int iCone, void *kkt, int typeKKT) {
+    return cone_build_schur((ConeCU *) cone, iCone, (KktCU *) kkt, typeKKT);
+}
+
+int hdsdpcu_cone_getbuffer(void *cone, int which, double *out) {
+    ConeCU *c = (ConeCU *) cone;
+    HD_CUDA(cudaMemcpy2DAsync(out, (size_t) c->n * 8, c->d_buf[which], (size_t) c->np * 8, (size_t) c->n * 8, c->n,
+                              cudaMemcpyDeviceToHost, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    return HD_OK;
+}
+int hdsdpcu_cone_getsinv(void *cone, double *out) {
+    ConeCU *c = (ConeCU *) cone;
+    HD_CUDA(cudaMemcpy2DAsync(out, (size_t) c->n * 8, c->d_sinv, (size_t) c->np * 8, (size_t) c->n * 8, c->n,
+                              cudaMemcpyDeviceToHost, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    return HD_OK;
+}
+int hdsdpcu_cone_getfactordiag(void *cone, int which, double *diag) {
+    ConeCU *c = (ConeCU *) cone;
+    DenseChol *f = (which == BUF_DUALVAR) ? c->factor : c->checker;
+    HD_CUDA(cudaMemcpy2DAsync(diag, 8, f->L, (size_t) (f->np + 1) * 8, 8, f->n, cudaMemcpyDeviceToHost, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    return HD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// B2: KKT
+// ------------------------------------------------------------------------------------------------
+int hdsdpcu_kkt_create(void **pkkt, int nRow) {
+    if (!pkkt) return HD_FAILED;
+    HD_CALL(ensure_ready());
+    KktCU *k = nullptr;
+    int rc = kkt_create(&k, nRow);
+    if (rc != HD_OK) return rc;
+    *pkkt = k;
+    return HD_OK;
+}
+int hdsdpcu_kkt_addcone(void *kkt, void *cone) {
+    KktCU *k = (KktCU *) kkt;
+    ConeCU *c = (ConeCU *) cone;
+    if (c->m != k->m) return HD_FAILED;
+    k->cones.push_back(c);
+    return HD_OK;
+}
+void hdsdpcu_kkt_destroy(void **pkkt) {
+    if (!pkkt || !*pkkt) return;
+    kkt_destroy((KktCU *) *pkkt);
+    *pkkt = nullptr;
+}
+int hdsdpcu_kkt_buildup(void *kkt, int typeKKT) { return kkt_build_up((KktCU *) kkt, typeKKT); }
+int hdsdpcu_kkt_clean(void *kkt, int typeKKT) { return kkt_clean((KktCU *) kkt, typeKKT); }
+int hdsdpcu_kkt_buildupextra_bound(void *kkt, const double *diagAdd, const double *asinvAdd, const double *asinvRdAdd, int typeKKT) {
+    if (typeKKT == KKT_PRIMAL) return HD_FAILED; // hdsdp_conic_bound.c:207-209
+    return kkt_add_host((KktCU *) kkt, typeKKT == KKT_CORRECTOR ? nullptr : diagAdd, asinvAdd, asinvRdAdd, nullptr, nullptr);
+}
+
+int hdsdpcu_lp_create(void **plp, int nRow, int nLpCol, const int *beg, const int *idx, const double *elem) {
+    // user data: CSC [nLpCol x (nRow + 1)], column 0 = objective, column k+1 = constraint k, row index = LP column
+    HD_CALL(ensure_ready());
+    std::vector<int> cnt(nLpCol + 1, 0);
+    for (int k = 0; k < nRow; ++k)
+        for (int e = beg[k + 1]; e < beg[k + 2]; ++e) cnt[idx[e] + 1] += 1;
+    for (int c = 0; c < nLpCol; ++c) cnt[c + 1] += cnt[c];
+    std::vector<int> ptr(cnt), rowidx(cnt[nLpCol]);
+    std::vector<double> val(cnt[nLpCol]);
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int k = 0; k < nRow; ++k)
+        for (int e = beg[k + 1]; e < beg[k + 2]; ++e) {
+            int p = fill[idx[e]]++;
+            rowidx[p] = k; val[p] = elem[e];
+        }
+    LpCU *lp = (LpCU *) calloc(1, sizeof(LpCU));
+    lp->m = nRow; lp->ncol = nLpCol;
+    HD_CUDA(cudaMalloc(&lp->d_colptr, sizeof(int) * (nLpCol + 1)));
+    HD_CUDA(cudaMalloc(&lp->d_rowidx, sizeof(int) * (rowidx.size() + 1)));
+    HD_CUDA(cudaMalloc(&lp->d_val, sizeof(double) * (val.size() + 1)));
+    HD_CUDA(cudaMalloc(&lp->d_sinv, sizeof(double) * (nLpCol + 1)));
+    HD_CUDA(cudaMemcpy(lp->d_colptr, ptr.data(), sizeof(int) * (nLpCol + 1), cudaMemcpyHostToDevice));
+    HD_CUDA(cudaMemcpy(lp->d_rowidx, rowidx.data(), sizeof(int) * rowidx.size(), cudaMemcpyHostToDevice));
+    HD_CUDA(cudaMemcpy(lp->d_val, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice));
+    *plp = lp;
+    return HD_OK;
+}
+void hdsdpcu_lp_destroy(void **plp) {
+    if (!plp || !*plp) return;
+    LpCU *lp = (LpCU *) *plp;
+    cudaFree(lp->d_colptr); cudaFree(lp->d_rowidx); cudaFree(lp->d_val); cudaFree(lp->d_sinv);
+    free(lp);
+    *plp = nullptr;
+}
+int hdsdpcu_kkt_buildupextra_lp(void *kkt, void *plp, const double *colDualInverse, double dualResidual, int typeKKT) {
+    LpCU *lp = (LpCU *) plp;
+    KktCU *k = (KktCU *) kkt;
+    if (lp->m != k->m) return HD_FAILED;
+    HD_CALL(kkt_add_lp(k, lp->ncol, lp->d_colptr, lp->d_rowidx, lp->d_val, colDualInverse, lp->d_sinv, dualResidual, typeKKT));
+    if (dualResidual != 0.0) { // dTraceSinv += sum 1/s  (hdsdp_conic_lp.c:276-279)
+        double add[4] = {0, 0, 0, 0};
+        for (int c = 0; c < lp->ncol; ++c) add[3] += colDualInverse[c];
+        HD_CALL(kkt_add_host(k, nullptr, nullptr, nullptr, nullptr, add));
+    }
+    return HD_OK;
+}
+int hdsdpcu_kkt_regularize(void *kkt, double reg) { return kkt_regularize((KktCU *) kkt, reg); }
+int hdsdpcu_kkt_export(void *kkt, double *a, double *ard, double *ac, double *cscs, double *cs, double *csrd, double *tr) {
+    return kkt_export((KktCU *) kkt, a, ard, ac, cscs, cs, csrd, tr);
+}
+int hdsdpcu_kkt_factorize(void *kkt) { return kkt_factorize((KktCU *) kkt, nullptr); }
+int hdsdpcu_kkt_solve(void *kkt, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, 1, rhs, lhs); }
+int hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, nRhs, rhs, lhs); }
+void hdsdpcu_kkt_registerpsdp(void *kkt, double **X) {
+    KktCU *k = (KktCU *) kkt;
+    k->primalX.assign(k->cones.size(), nullptr);
+    if (X) for (size_t i = 0; i < k->cones.size(); ++i) k->primalX[i] = X[i];
+}
+int hdsdpcu_kkt_getmatrix(void *kkt, double *M) { return kkt_get_matrix((KktCU *) kkt, M); }
+int hdsdpcu_kkt_padded_dim(void *kkt) { return ((KktCU *) kkt)->mp; }
+double *hdsdpcu_kkt_matrix_dev(void *kkt) { return ((KktCU *) kkt)->d_M; }
+double *hdsdpcu_kkt_asinv_dev(void *kkt) { return ((KktCU *) kkt)->d_asinv; }
+int hdsdpcu_kkt_solve_dev(void *kkt, int nRhs, double *d_x) { return kkt_solve_dev((KktCU *) kkt, d_x, nRhs); }
+int hdsdpcu_kkt_setshard(void *kkt, int rank, int nRanks) {
+    KktCU *k = (KktCU *) kkt;
+    if (nRanks < 1 || rank < 0 || rank >= nRanks) return HD_FAILED;
+    k->rank = rank; k->nranks = nRanks;
+    return HD_OK;
+}
+
+int hdsdpcu_dgemm_nt_dev(int M, int N, int K, double alpha, const double *dA, long lda, const double *dB, long ldb,
+                         double beta, double *dC, long ldc, int lowerOnly) {
+    HD_CALL(ensure_ready());
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.A = dA; g.lda = lda; g.B = dB; g.ldb = ldb; g.C = dC; g.ldc = ldc;
+    g.alpha = alpha; g.beta = beta; g.flags = lowerOnly ? HD_GEMM_LOWER : 0;
+    return hd_gemm_nt(g_stream, g);
+}
+
+} // extern "C"

@@ -1,0 +1,374 @@
+// hdsdp_b200/csrc/chol.cu -- dense FP64 Cholesky / inverse / triangular solves on sm_100a.
+//
+// Replaces the LAPACK calls behind the reference's dense linear-system back-end
+// (reference linalg/hdsdp_linsolver.c: dpotrf :1096, dtrsm :1158/:1184, dpotrs :1210,
+//  dpotri + symmetrise :1238-1260, diag extraction :1227).
+//
+// Algorithm: cache-oblivious *recursive* right-looking Cholesky on a matrix padded to a multiple
+// of 128.  All O(n^3) work is the DMMA GEMM of gemm_nt.cu:
+//     potrf(A)      : potrf(A11); A21 <- A21 L11^-T; A22 -= A21 A21^T (lower tiles); potrf(A22)
+//     trsm(B, L)    : B1 <- B1 L11^-T; B2 -= B1 L21^T; B2 <- B2 L22^-T
+//     leaf (128)    : one CTA factors the 128x128 block in shared memory and also emits its
+//                     explicit inverse, so every leaf triangular solve is again a GEMM / GEMV.
+// The recursion runs on the host and only enqueues kernels on one stream; shapes are fixed per
+// matrix size, so a whole factorisation can be captured into a CUDA graph by the caller.
+#include "common.h"
+#include <cmath>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Leaf: Cholesky of one 128x128 block + its inverse.  One CTA, 512 threads, 128 KB smem.
+// ------------------------------------------------------------------------------------------
+constexpr int LEAF_THREADS = 512;
+
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+potf2_leaf_kernel(double *A, long lda, double *Dinv, int *info, int base) {
+    extern __shared__ __align__(16) double Ls[]; // 128 x 128 column-major, + 128 column buffer
+    double *colbuf = Ls + HD_LEAF * HD_LEAF;
+    const int tid = threadIdx.x;
+    // load lower triangle (upper := 0)
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += LEAF_THREADS) {
+        int i = e & 127, k = e >> 7;
+        Ls[e] = (i >= k) ? A[(long) k * lda + i] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < HD_LEAF; ++j) {
+        double d = Ls[j * HD_LEAF + j];
+        bool bad = !(d > 0.0) || isinf(d);
+        if (bad) {
+            if (tid == 0) atomicCAS(info, 0, base + j + 1);
+            d = 1.0;
+        }
+        double r = sqrt(d);
+        double rinv = 1.0 / r;
+        __syncthreads(); // everyone has read the pivot
+        for (int i = j + tid; i < HD_LEAF; i += LEAF_THREADS) {
+            Ls[j * HD_LEAF + i] = (i == j) ? r : Ls[j * HD_LEAF + i] * rinv;
+        }
+        __syncthreads();
+        // trailing update of columns k = j+1 .. 127, rows i >= k : thread -> (row ti, column phase tk)
+        {
+            const int ti = tid & 127, tk = tid >> 7;
+            if (ti > j) {
+                const double lij = Ls[j * HD_LEAF + ti];
+                for (int k = j + 1 + tk; k <= ti; k += 4) Ls[k * HD_LEAF + ti] -= lij * Ls[j * HD_LEAF + k];
+            }
+        }
+        __syncthreads();
+    }
+    // write back L (lower only; strict upper of the global block is left untouched)
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += LEAF_THREADS) {
+        int i = e & 127, k = e >> 7;
+        if (i >= k) A[(long) k * lda + i] = Ls[e];
+    }
+    __syncthreads();
+    // in-place inverse of the lower-triangular factor (column sweep from the last column):
+    //   inv[j][j] = 1/L[j][j];  inv[j+1:, j] = -inv[j][j] * (inv[j+1:, j+1:] * L[j+1:, j])
+    // 4 threads cooperate on one row (k-range split), 128 rows x 4 = 512 threads.
+    const int row = tid >> 2, part = tid & 3;
+    for (int j = HD_LEAF - 1; j >= 0; --j) {
+        if (tid < HD_LEAF) colbuf[tid] = Ls[j * HD_LEAF + tid]; // copy column j of L
+        __syncthreads();
+        double djj = 1.0 / colbuf[j];
+        double s = 0.0;
+        if (row > j) {
+            // x_row = sum_{k=j+1}^{row} inv[row][k] * L[k][j]
+            for (int k = j + 1 + part; k <= row; k += 4) s += Ls[k * HD_LEAF + row] * colbuf[k];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) {
+            if (row > j) Ls[j * HD_LEAF + row] = -djj * s;
+            else if (row == j) Ls[j * HD_LEAF + row] = djj;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += LEAF_THREADS) Dinv[e] = Ls[e]; // upper part is exactly 0
+}
+
+// X leaf (upper triangular) = Dinv^T
+__global__ void leaf_transpose_kernel(const double *__restrict__ Dinv, double *X, long ldx) {
+    __shared__ double t[32][33];
+    int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    int tx = threadIdx.x, ty = threadIdx.y; // 32 x 8
+    for (int r = ty; r < 32; r += 8) t[r][tx] = Dinv[(long) (by + r) * HD_LEAF + bx + tx]; // t[k][i] = Dinv[i,k]
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) X[(long) (bx + r) * ldx + by + tx] = t[tx][r]; // X[k, i] = Dinv[i, k]
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMV helpers for the vector triangular solves (HBM-bound; algorithmic bytes = 8 per entry of L)
+// ------------------------------------------------------------------------------------------
+constexpr int GV_COLS = 256;
+
+// y[rows] -= A[rows x cols] * x[cols]     grid (rows/128, ceil(cols/GV_COLS)), 128 threads
+__global__ void __launch_bounds__(128) gemv_n_sub_kernel(const double *__restrict__ A, long lda, int cols,
+                                                        const double *x, double *y) {
+    __shared__ double xs[GV_COLS];
+    const int c0 = blockIdx.y * GV_COLS;
+    const int nc = min(GV_COLS, cols - c0);
+    for (int c = threadIdx.x; c < nc; c += 128) xs[c] = x[c0 + c];
+    __syncthreads();
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    const double *a = A + (long) c0 * lda + r;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int c = 0;
+    for (; c + 4 <= nc; c += 4) {
+        s0 += a[(long) (c + 0) * lda] * xs[c + 0];
+        s1 += a[(long) (c + 1) * lda] * xs[c + 1];
+        s2 += a[(long) (c + 2) * lda] * xs[c + 2];
+        s3 += a[(long) (c + 3) * lda] * xs[c + 3];
+    }
+    for (; c < nc; ++c) s0 += a[(long) c * lda] * xs[c];
+    atomicAdd(&y[r], -((s0 + s1) + (s2 + s3)));
+}
+
+// y[cols] -= A[rows x cols]^T * x[rows]   grid (cols/128, ceil(rows/1024)), 256 threads (8 warps x 16 cols)
+constexpr int GT_ROWS = 1024;
+__global__ void __launch_bounds__(256) gemv_t_sub_kernel(const double *__restrict__ A, long lda, int rows,
+                                                        const double *x, double *y) {
+    __shared__ double xs[GT_ROWS];
+    const int r0 = blockIdx.y * GT_ROWS;
+    const int nr = min(GT_ROWS, rows - r0);
+    for (int r = threadIdx.x; r < nr; r += 256) xs[r] = x[r0 + r];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int cc = 0; cc < 16; ++cc) {
+        const int c = blockIdx.x * 128 + warp * 16 + cc;
+        const double *a = A + (long) c * lda + r0;
+        double s = 0.0;
+        for (int r = lane; r < nr; r += 32) s += a[r] * xs[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) atomicAdd(&y[c], -s);
+    }
+}
+
+// x[128] <- Dinv * x  (trans == 0)  or  Dinv^T * x (trans == 1);  one CTA of 128 threads per rhs
+__global__ void __launch_bounds__(128) leaf_solve_kernel(const double *__restrict__ Dinv, double *x, long ldx, int trans) {
+    __shared__ double xs[HD_LEAF];
+    double *xv = x + (long) blockIdx.x * ldx;
+    xs[threadIdx.x] = xv[threadIdx.x];
+    __syncthreads();
+    if (!trans) {
+        const int i = threadIdx.x;
+        double s = 0.0;
+        for (int k = 0; k <= i; ++k) s += Dinv[k * HD_LEAF + i] * xs[k];
+        xv[i] = s;
+    } else {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int ii = 0; ii < 32; ++ii) {
+            const int i = warp * 32 + ii; // out_i = sum_{k>=i} Dinv[k,i] x_k
+            double s = 0.0;
+            for (int k = i + lane; k < HD_LEAF; k += 32) s += Dinv[i * HD_LEAF + k] * xs[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) xv[i] = s;
+        }
+    }
+}
+
+__global__ void logdet_kernel(const double *L, long ld, int n, double *out, double *diag) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        double d = L[(long) i * ld + i];
+        if (diag) diag[i] = d;
+        s += log(d);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && out) *out = 2.0 * red[0];
+}
+
+bool g_leaf_attr = false;
+const int LEAF_SMEM = (HD_LEAF * HD_LEAF + HD_LEAF) * 8;
+
+int split_leaves(int n) { return ((n / HD_LEAF) / 2) * HD_LEAF; } // n1 (multiple of 128, >= 128 when n >= 256)
+
+// B (rows x n, ld ldb) <- B * L^-T,  L n x n lower (ld ldl), dinv = inverse leaves of L
+int trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, long ldl, int n, const double *dinv) {
+    if (rows <= 0) return HD_OK;
+    if (n == HD_LEAF) {
+        GemmArgs g{};
+        g.M = rows; g.N = HD_LEAF; g.K = HD_LEAF;
+        g.A = B; g.lda = ldb; g.B = dinv; g.ldb = HD_LEAF; g.C = B; g.ldc = ldb;
+        g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
+        return hd_gemm_nt(st, g); // in place: each CTA reads exactly the rows it later writes
+    }
+    int n1 = split_leaves(n), n2 = n - n1;
+    HD_CALL(trsm_rec(st, B, ldb, rows, L, ldl, n1, dinv));
+    GemmArgs g{};
+    g.M = rows; g.N = n2; g.K = n1;
+    g.A = B; g.lda = ldb; g.B = L + n1; g.ldb = ldl; g.C = B + (long) n1 * ldb; g.ldc = ldb;
+    g.alpha = -1.0; g.beta = 1.0; g.flags = 0;
+    HD_CALL(hd_gemm_nt(st, g));
+    return trsm_rec(st, B + (long) n1 * ldb, ldb, rows, L + (long) n1 * ldl + n1, ldl, n2,
+                    dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF);
+}
+
+int potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base) {
+    if (n == HD_LEAF) {
+        HDK(potf2_leaf_kernel)<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, dinv, info, base);
+        HD_CUDA(cudaGetLastError());
+        return HD_OK;
+    }
+    int n1 = split_leaves(n), n2 = n - n1;
+    HD_CALL(potrf_rec(st, A, lda, n1, dinv, info, base));
+    HD_CALL(trsm_rec(st, A + n1, lda, n2, A, lda, n1, dinv));
+    GemmArgs g{};
+    g.M = n2; g.N = n2; g.K = n1;
+    g.A = A + n1; g.lda = lda; g.B = A + n1; g.ldb = lda; g.C = A + (long) n1 * lda + n1; g.ldc = lda;
+    g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+    HD_CALL(hd_gemm_nt(st, g));
+    return potrf_rec(st, A + (long) n1 * lda + n1, lda, n2, dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF, info,
+                     base + n1);
+}
+
+// X (n x n upper triangular, ld ldx) = L^-T.   Block formula:
+//   X11 = L11^-T, X22 = L22^-T, X12 = -(X11 L21^T) L22^-T  (the right factor applied by trsm_rec)
+int invert_rec(cudaStream_t st, const double *L, long ldl, int n, const double *dinv, double *X, long ldx) {
+    if (n == HD_LEAF) {
+        HDK(leaf_transpose_kernel)<<<dim3(4, 4), dim3(32, 8), 0, st>>>(dinv, X, ldx);
+        HD_CUDA(cudaGetLastError());
+        return HD_OK;
+    }
+    int n1 = split_leaves(n), n2 = n - n1;
+    const double *dinv2 = dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF;
+    HD_CALL(invert_rec(st, L, ldl, n1, dinv, X, ldx));
+    HD_CALL(invert_rec(st, L + (long) n1 * ldl + n1, ldl, n2, dinv2, X + (long) n1 * ldx + n1, ldx));
+    GemmArgs g{};
+    g.M = n1; g.N = n2; g.K = n1;
+    g.A = X; g.lda = ldx; g.B = L + n1; g.ldb = ldl; g.C = X + (long) n1 * ldx; g.ldc = ldx;
+    g.alpha = -1.0; g.beta = 0.0; g.flags = 0;
+    HD_CALL(hd_gemm_nt(st, g));
+    return trsm_rec(st, X + (long) n1 * ldx, ldx, n1, L + (long) n1 * ldl + n1, ldl, n2, dinv2);
+}
+
+// L x = b (in place), nrhs right-hand sides with stride ldx
+int fsolve_rec(cudaStream_t st, const double *L, long ldl, int n, const double *dinv, double *x, int nrhs, long ldx) {
+    if (n == HD_LEAF) {
+        HDK(leaf_solve_kernel)<<<nrhs, 128, 0, st>>>(dinv, x, ldx, 0);
+        HD_CUDA(cudaGetLastError());
+        return HD_OK;
+    }
+    int n1 = split_leaves(n), n2 = n - n1;
+    HD_CALL(fsolve_rec(st, L, ldl, n1, dinv, x, nrhs, ldx));
+    for (int r = 0; r < nrhs; ++r) {
+        dim3 grid(n2 / 128, (n1 + GV_COLS - 1) / GV_COLS);
+        HDK(gemv_n_sub_kernel)<<<grid, 128, 0, st>>>(L + n1, ldl, n1, x + r * ldx, x + r * ldx + n1);
+    }
+    HD_CUDA(cudaGetLastError());
+    return fsolve_rec(st, L + (long) n1 * ldl + n1, ldl, n2, dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF,
+                      x + n1, nrhs, ldx);
+}
+
+// L^T x = b (in place)
+int bsolve_rec(cudaStream_t st, const double *L, long ldl, int n, const double *dinv, double *x, int nrhs, long ldx) {
+    if (n == HD_LEAF) {
+        HDK(leaf_solve_kernel)<<<nrhs, 128, 0, st>>>(dinv, x, ldx, 1);
+        HD_CUDA(cudaGetLastError());
+        return HD_OK;
+    }
+    int n1 = split_leaves(n), n2 = n - n1;
+    HD_CALL(bsolve_rec(st, L + (long) n1 * ldl + n1, ldl, n2, dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF,
+                       x + n1, nrhs, ldx));
+    for (int r = 0; r < nrhs; ++r) {
+        dim3 grid(n1 / 128, (n2 + GT_ROWS - 1) / GT_ROWS);
+        HDK(gemv_t_sub_kernel)<<<grid, 256, 0, st>>>(L + n1, ldl, n2, x + r * ldx + n1, x + r * ldx);
+    }
+    HD_CUDA(cudaGetLastError());
+    return bsolve_rec(st, L, ldl, n1, dinv, x, nrhs, ldx);
+}
+
+} // namespace
+
+int chol_create(DenseChol **pc, int n) {
+    if (n <= 0) return HD_FAILED;
+    DenseChol *c = (DenseChol *) calloc(1, sizeof(DenseChol));
+    if (!c) return HD_MEMORY;
+    c->n = n;
+    c->np = hd_pad(n);
+    size_t bytes = (size_t) c->np * c->np * sizeof(double);
+    if (cudaMalloc(&c->L, bytes) != cudaSuccess) { free(c); cudaGetLastError(); return HD_MEMORY; }
+    if (cudaMalloc(&c->Dinv, (size_t) c->np * HD_LEAF * sizeof(double)) != cudaSuccess) {
+        cudaFree(c->L); free(c); cudaGetLastError(); return HD_MEMORY;
+    }
+    if (cudaMalloc(&c->dinfo, sizeof(int)) != cudaSuccess || cudaMallocHost(&c->hinfo, sizeof(int)) != cudaSuccess) {
+        cudaFree(c->L); cudaFree(c->Dinv); free(c); cudaGetLastError(); return HD_MEMORY;
+    }
+    c->work = nullptr;
+    c->factored = false;
+    *pc = c;
+    return HD_OK;
+}
+
+void chol_destroy(DenseChol *c) {
+    if (!c) return;
+    cudaFree(c->L);
+    cudaFree(c->Dinv);
+    cudaFree(c->dinfo);
+    cudaFreeHost(c->hinfo);
+    if (c->work) cudaFree(c->work);
+    free(c);
+}
+
+int chol_ensure_work(DenseChol *c) {
+    if (c->work) return HD_OK;
+    HD_CUDA(cudaMalloc(&c->work, (size_t) c->np * c->np * sizeof(double)));
+    return HD_OK;
+}
+
+int chol_load_dev(cudaStream_t st, DenseChol *c, const double *dS, long lds) {
+    HD_CALL(hd_copy2d(st, c->L, c->np, dS, lds, c->n, c->n));
+    HD_CALL(hd_pad_identity(st, c->L, c->np, c->n, c->np));
+    c->factored = false;
+    return HD_OK;
+}
+
+int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
+    if (!g_leaf_attr) {
+        HD_CUDA(cudaFuncSetAttribute(potf2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+        g_leaf_attr = true;
+    }
+    HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
+    HD_CALL(potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0));
+    HD_CUDA(cudaMemcpyAsync(c->hinfo, c->dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HD_CUDA(cudaStreamSynchronize(st));
+    int inf = *c->hinfo;
+    if (inf > c->n) inf = 0; // padding pivots are exactly 1
+    if (info) *info = inf;
+    c->factored = (inf == 0);
+    return HD_OK;
+}
+
+int chol_invert(cudaStream_t st, DenseChol *c, double *inv) {
+    HD_CALL(chol_ensure_work(c));
+    // X = L^-T (upper triangular) in work; blocks below the diagonal leaves must read as zero
+    HD_CUDA(cudaMemsetAsync(c->work, 0, (size_t) c->np * c->np * sizeof(double), st));
+    HD_CALL(invert_rec(st, c->L, c->np, c->np, c->Dinv, c->work, c->np));
+    GemmArgs g{};
+    g.M = c->np; g.N = c->np; g.K = c->np;
+    g.A = c->work; g.lda = c->np; g.B = c->work; g.ldb = c->np; g.C = inv; g.ldc = c->np;
+    g.alpha = 1.0; g.beta = 0.0; g.flags = HD_GEMM_LOWER | HD_GEMM_KTRI_MAX;
+    HD_CALL(hd_gemm_nt(st, g));
+    return hd_symmetrize_lower(st, inv, c->np, c->np);
+}
+
+int chol_fsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx) {
+    return fsolve_rec(st, c->L, c->np, c->np, c->Dinv, x, nrhs, ldx);
+}
+int chol_bsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx) {
+    return bsolve_rec(st, c->L, c->np, c->np, c->Dinv, x, nrhs, ldx);
+}
+
+int chol_logdet(cudaStream_t st, DenseChol *c, double *dlogdet, double *ddiag) {
+    HDK(logdet_kernel)<<<1, 256, 0, st>>>(c->L, c->np, c->n, dlogdet, ddiag);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}

@@ -1,0 +1,108 @@
+// hdsdp_b200/csrc/common.h -- shared declarations of the sm_100a hot-path library.
+//
+// Everything here is FP64, column-major, and sized in "leaves" of HD_LEAF = 128 rows/cols:
+// every dense matrix the library owns is padded to a multiple of 128 in both dimensions
+// (identity / zero padding) so the DMMA tile kernels never need edge predicates.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#define HD_LEAF 128
+
+// every kernel launch of the library goes through HDK(kernel)<<<...>>> so launches can be counted
+extern long g_hd_launches;
+#define HDK(k) (++g_hd_launches, k)
+
+// hdsdp_retcode values (reference interface/hdsdp.h:42-48)
+#define HD_OK 0
+#define HD_FAILED 1
+#define HD_MEMORY 2
+
+#define HD_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fprintf(stderr, "[hdsdpcu] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_),    \
+                    __FILE__, __LINE__, cudaGetErrorString(e_));                               \
+            return (e_ == cudaErrorMemoryAllocation) ? HD_MEMORY : HD_FAILED;                  \
+        }                                                                                      \
+    } while (0)
+
+#define HD_CUDA_VOID(call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fprintf(stderr, "[hdsdpcu] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_),    \
+                    __FILE__, __LINE__, cudaGetErrorString(e_));                               \
+        }                                                                                      \
+    } while (0)
+
+#define HD_CALL(call)                     \
+    do {                                  \
+        int rc_ = (call);                 \
+        if (rc_ != HD_OK) return rc_;     \
+    } while (0)
+
+static inline int hd_pad(int n) { return ((n + HD_LEAF - 1) / HD_LEAF) * HD_LEAF; }
+
+// ---------------------------------------------------------------------------------------------
+// DMMA GEMM:  C (M x N) = alpha * A (M x K) * B (N x K)^T + beta * C      (all column-major)
+// M, N multiples of 128; K multiple of 16; pointers 16-byte aligned; ld* even.
+// ---------------------------------------------------------------------------------------------
+enum : int {
+    HD_GEMM_LOWER = 1,      // only tiles that intersect the lower triangle (m >= n); strict-upper entries untouched
+    HD_GEMM_KTRI_MAX = 2,   // operands are "upper triangular in (row,k)": start k at min(m0,n0)... see gemm_nt.cu
+    HD_GEMM_EPI_HADSQ = 4,  // epilogue C += sa[m]*sb[n]*acc^2 (rank-one Schur, M2)
+};
+
+struct GemmArgs {
+    int M, N, K;
+    const double *A; long lda;
+    const double *B; long ldb;
+    double *C; long ldc;
+    double alpha, beta;
+    int flags;
+    const double *sa;   // HADSQ: scale over m
+    const double *sb;   // HADSQ: scale over n
+};
+
+int hd_gemm_nt(cudaStream_t st, const GemmArgs &g);
+int hd_num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// Dense SPD factorisation object (device resident).
+// ---------------------------------------------------------------------------------------------
+struct DenseChol {
+    int n;        // logical dimension
+    int np;       // padded dimension (multiple of 128) == leading dimension
+    double *L;    // np x np factor (lower); strict upper of diagonal leaves is garbage
+    double *Dinv; // (np/128) inverse leaves, each 128 x 128 column-major lower triangular
+    int *dinfo;   // device: 0 ok, else 1-based index of the first non-positive pivot
+    int *hinfo;   // pinned host mirror
+    double *work; // np x np workspace (inverse / staging), allocated lazily
+    bool factored;
+};
+
+int chol_create(DenseChol **pc, int n);
+void chol_destroy(DenseChol *c);
+int chol_ensure_work(DenseChol *c);
+// copy an n x n column-major device matrix (leading dim lds) into the padded factor buffer
+int chol_load_dev(cudaStream_t st, DenseChol *c, const double *dS, long lds);
+// factor whatever is in c->L ; *info: 0 = SPD, >0 = not positive definite (LAPACK dpotrf semantics)
+int chol_factor(cudaStream_t st, DenseChol *c, int *info);
+// inv (np x np, ld = np, full symmetric) = (L L^T)^-1 ; uses c->work
+int chol_invert(cudaStream_t st, DenseChol *c, double *inv);
+// in-place triangular solves on nrhs device vectors (each of length >= n, stride ldx)
+int chol_fsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx);
+int chol_bsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx);
+// sum_i log(L_ii) * 2 written to *dlogdet (device) ; diag(L) to ddiag (device, n) if non-null
+int chol_logdet(cudaStream_t st, DenseChol *c, double *dlogdet, double *ddiag);
+
+// small utility kernels (util.cu)
+int hd_set_identity(cudaStream_t st, double *A, long lda, int n);
+int hd_pad_identity(cudaStream_t st, double *A, long lda, int n, int np);
+int hd_symmetrize_lower(cudaStream_t st, double *A, long lda, int n);
+int hd_scale_vec(cudaStream_t st, double *x, int m, double a);
+int hd_copy2d(cudaStream_t st, double *dst, long ldd, const double *src, long lds, int rows, int cols);

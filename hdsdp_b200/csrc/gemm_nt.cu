@@ -1,0 +1,224 @@
+// hdsdp_b200/csrc/gemm_nt.cu -- FP64 tensor-core (DMMA) tile GEMM for sm_100a.
+//
+//   C (M x N) = alpha * A (M x K) * B (N x K)^T + beta * C          all column-major
+//
+// This one kernel carries every O(n^3) operation of the hot path:
+//   * trailing updates / panel solves of the recursive Cholesky of M and S
+//     (replaces dpotrf/dtrsm behind reference linalg/hdsdp_linsolver.c:1096,1158,1184),
+//   * S^-1 = X X^T with X = L^-T  (replaces dpotri, hdsdp_linsolver.c:1250),
+//   * the rank-one Schur products V^T = A^T S^-1 and G = A^T V with the Hadamard-square
+//     epilogue M_ij += s_i s_j G_ij^2 (reference M2 column builder, hdsdp_conic_sdp.c:687-778).
+//
+// Design (B200): FP64 MMA exists only as mma.sync m8n8k4 (SASS DMMA.8x8x4; the sm_90 m16n8k*
+// shapes lower to the same instruction on sm_100a, and tcgen05 has no f64 kind), so this is a
+// register-accumulator kernel: 128x128x16 CTA tile, 8 warps of 64(m) x 32(n), 4-stage
+// cp.async (LDGSTS 16 B) pipeline, shared tiles stored k-major with a row stride of 132
+// doubles so the fragment loads (address = tig*132 + gid) are bank-conflict free.
+// The MMA is issued "transposed" (MMA-M runs along n, MMA-N along m) so each thread owns two
+// m-consecutive doubles per accumulator pair and the epilogue is 16-byte vector traffic on the
+// column-major C.  Grid: 1-D, grouped 8x8 super-tiles for L2 reuse of the A/B panels.
+#include "common.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int LDS_ = 132;                    // padded smem row stride (doubles)
+constexpr int STAGE_DOUBLES = 2 * BK * LDS_; // A tile + B tile
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+constexpr int GROUP = 8;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct TileMap {
+    int tiles_m, tiles_n, lower;
+};
+
+// linear CTA index -> (tm, tn); returns false if this CTA has no tile
+__device__ __forceinline__ bool map_tile(const TileMap &tmap, int bid, int &tm, int &tn) {
+    const int gsq = GROUP * GROUP;
+    int super = bid / gsq, within = bid % gsq;
+    int sm_, sn_;
+    if (tmap.lower) {
+        // super-tiles of the lower triangle of a square super-grid, row by row
+        int s = (int) ((sqrtf(8.0f * (float) super + 1.0f) - 1.0f) * 0.5f);
+        while ((s + 1) * (s + 2) / 2 <= super) ++s;
+        while (s * (s + 1) / 2 > super) --s;
+        sm_ = s;
+        sn_ = super - s * (s + 1) / 2;
+    } else {
+        int super_n = (tmap.tiles_n + GROUP - 1) / GROUP;
+        sm_ = super / super_n;
+        sn_ = super % super_n;
+    }
+    tm = sm_ * GROUP + within % GROUP;
+    tn = sn_ * GROUP + within / GROUP;
+    if (tm >= tmap.tiles_m || tn >= tmap.tiles_n) return false;
+    if (tmap.lower && tn > tm) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
+    extern __shared__ __align__(16) double smem[];
+    int tm, tn;
+    if (!map_tile(tmap, blockIdx.x, tm, tn)) return;
+    const int m0 = tm * BM, n0 = tn * BN;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = (warp & 1) * 64;  // warp offset along m
+    const int wn = (warp >> 1) * 32; // warp offset along n
+
+    int k_lo = 0;
+    if (g.flags & HD_GEMM_KTRI_MAX) k_lo = max(m0, n0); // X[i,k] == 0 for k < i on both operands
+    const int nk = (g.K - k_lo) / BK;
+
+    const double *Ag = g.A + (long) k_lo * g.lda + m0;
+    const double *Bg = g.B + (long) k_lo * g.ldb + n0;
+
+    // cp.async mapping: each operand stage = 16 k-rows x 128 doubles = 1024 16-byte chunks
+    auto load_stage = [&](int stage, int kt) {
+        double *As = smem + stage * STAGE_DOUBLES;
+        double *Bs = As + BK * LDS_;
+        const double *a = Ag + (long) kt * BK * g.lda;
+        const double *b = Bg + (long) kt * BK * g.ldb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int c = tid + i * 256;
+            int kr = c >> 6, mc = (c & 63) * 2;
+            cp_async16(As + kr * LDS_ + mc, a + (long) kr * g.lda + mc);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int c = tid + i * 256;
+            int kr = c >> 6, nc = (c & 63) * 2;
+            cp_async16(Bs + kr * LDS_ + nc, b + (long) kr * g.ldb + nc);
+        }
+    };
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nxt = kt + STAGES - 1;
+            if (nxt < nk) load_stage(nxt % STAGES, nxt);
+            cp_async_commit();
+        }
+        const double *As = smem + (kt % STAGES) * STAGE_DOUBLES;
+        const double *Bs = As + BK * LDS_;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double bf[4], af[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bf[i] = Bs[(kk + tig) * LDS_ + wn + 8 * i + gid];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) af[j] = As[(kk + tig) * LDS_ + wm + 8 * j + gid];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], bf[i], af[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread owns C[m .. m+1][n] with n = n0+wn+8i+gid, m = m0+wm+8j+2*tig
+    const bool lower = (g.flags & HD_GEMM_LOWER) != 0;
+    const bool hadsq = (g.flags & HD_GEMM_EPI_HADSQ) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + wn + 8 * i + gid;
+        double sbn = hadsq ? g.sb[n] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int m = m0 + wm + 8 * j + 2 * tig;
+            if (lower && m + 1 < n) continue;
+            double2 *cp = reinterpret_cast<double2 *>(g.C + (long) n * g.ldc + m);
+            double2 v;
+            if (hadsq) {
+                double2 old = *cp;
+                v.x = old.x + g.sa[m] * sbn * acc[i][j][0] * acc[i][j][0];
+                v.y = old.y + g.sa[m + 1] * sbn * acc[i][j][1] * acc[i][j][1];
+            } else if (g.beta == 0.0) {
+                v.x = g.alpha * acc[i][j][0];
+                v.y = g.alpha * acc[i][j][1];
+            } else {
+                double2 old = *cp;
+                v.x = g.alpha * acc[i][j][0] + g.beta * old.x;
+                v.y = g.alpha * acc[i][j][1] + g.beta * old.y;
+            }
+            if (lower && m < n) {
+                // m == n-1: only the second element (m+1 == n) is in the lower triangle
+                g.C[(long) n * g.ldc + m + 1] = v.y;
+            } else {
+                *cp = v;
+            }
+        }
+    }
+}
+
+int g_num_sms = 0;
+bool g_attr_set = false;
+
+} // namespace
+
+int hd_num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
+    if (g.M <= 0 || g.N <= 0) return HD_OK;
+    if (g.M % BM || g.N % BN || g.K % BK) {
+        fprintf(stderr, "[hdsdpcu] gemm_nt: unpadded shape %d %d %d\n", g.M, g.N, g.K);
+        return HD_FAILED;
+    }
+    if (!g_attr_set) {
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        g_attr_set = true;
+    }
+    TileMap tmap;
+    tmap.tiles_m = g.M / BM;
+    tmap.tiles_n = g.N / BN;
+    tmap.lower = (g.flags & HD_GEMM_LOWER) ? 1 : 0;
+    long nsuper;
+    if (tmap.lower) {
+        if (g.M != g.N) return HD_FAILED;
+        long s = (tmap.tiles_m + GROUP - 1) / GROUP;
+        nsuper = s * (s + 1) / 2;
+    } else {
+        nsuper = (long) ((tmap.tiles_m + GROUP - 1) / GROUP) * ((tmap.tiles_n + GROUP - 1) / GROUP);
+    }
+    long nblocks = nsuper * GROUP * GROUP;
+    HDK(dgemm_nt_kernel)<<<(unsigned) nblocks, 256, SMEM_BYTES, st>>>(g, tmap);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}

@@ -1,0 +1,152 @@
+/*
+ * include/hdsdpcu.h -- C ABI of libhdsdp_cuda.so, the B200 (sm_100a) implementation of HDSDP's
+ * per-iteration Newton-system hot path (dual slack S, its Cholesky factor and inverse; the Schur
+ * complement M_ij = <A_i, S^-1 A_j S^-1>; the dense FP64 Cholesky factorisation and solve of M).
+ *
+ * Plain C: opaque handles, pointers and sizes only.  Unless a name ends in _dev, every pointer is a
+ * HOST pointer with exactly the meaning it has in the reference interface it replaces, so the ANSI-C
+ * solver can bind these entry points directly (see INTEGRATION.md for the three hook sites).
+ * Return values are the reference's hdsdp_retcode (interface/hdsdp.h:42-48): 0 OK, 1 FAILED, 2 MEMORY.
+ * There is no CPU fallback: every compute entry point fails (1) when no CUDA device is usable.
+ *
+ * Dense matrices are column-major, full n x n storage with the LOWER triangle meaningful
+ * (reference FULL_ENTRY, interface/hdsdp_utils.h:53).
+ */
+#ifndef HDSDPCU_H
+#define HDSDPCU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------
+ * Runtime
+ * ------------------------------------------------------------------------------------------- */
+int hdsdpcu_init(int device);            /* select the device, create the library stream; 1 if no GPU */
+int hdsdpcu_device_count(void);          /* 0 without a usable GPU (never touches the device otherwise) */
+void *hdsdpcu_stream(void);              /* cudaStream_t all kernels are launched on (for CUDA-event timing) */
+int hdsdpcu_sync(void);
+const char *hdsdpcu_version(void);
+/* count of kernel launches issued by this library since the last reset (bench.py "gpu_launches") */
+long hdsdpcu_launch_count(int reset);
+
+/* ---------------------------------------------------------------------------------------------
+ * B1 -- dense linear-system back-end.  One-for-one replacement of the 11 function pointers of
+ * hdsdp_linsys_fp (reference linalg/def_hdsdp_linsolver.h:40-63) as implemented for LAPACK by
+ * lapackLinSolver* (reference linalg/hdsdp_linsolver.c:1044-1286).  Same argument meaning:
+ *   numeric / psdcheck : elem = nCol x nCol column-major, lower triangle read, NOT modified
+ *   fsolve / bsolve    : L \ rhs, L' \ rhs ; sol == NULL means in place        (:1146, :1172)
+ *   solve              : (L L') \ rhs                                          (:1198)
+ *   getdiag            : diag(L)                                               (:1227)
+ *   invert             : full symmetric inverse into fullInv, aux unused       (:1238)
+ * "not positive definite" is not an error: psdcheck sets *isPsd = 0 and returns 0; numeric returns 1
+ * exactly where dpotrf's info != 0 makes the reference return FAILED (:1099-1103).
+ * ------------------------------------------------------------------------------------------- */
+int  hdsdpcu_linsys_create(void **pchol, int nCol);                                   /* cholCreate  */
+void hdsdpcu_linsys_setparam(void *chol, void *param);                                /* cholSetParam (no-op) */
+int  hdsdpcu_linsys_symbolic(void *chol, int *colBeg, int *colIdx);                   /* cholSymbolic (no-op) */
+int  hdsdpcu_linsys_numeric(void *chol, int *colBeg, int *colIdx, double *elem);      /* cholNumeric */
+int  hdsdpcu_linsys_psdcheck(void *chol, int *colBeg, int *colIdx, double *elem, int *isPsd); /* cholPsdCheck */
+void hdsdpcu_linsys_fsolve(void *chol, int nRhs, double *rhs, double *sol);           /* cholFSolve  */
+void hdsdpcu_linsys_bsolve(void *chol, int nRhs, double *rhs, double *sol);           /* cholBSolve  */
+int  hdsdpcu_linsys_solve(void *chol, int nRhs, double *rhs, double *sol);            /* cholSolve   */
+int  hdsdpcu_linsys_getdiag(void *chol, double *diag);                                /* cholGetDiag */
+void hdsdpcu_linsys_invert(void *chol, double *fullInv, double *aux);                 /* cholInvert  */
+void hdsdpcu_linsys_destroy(void **pchol);                                            /* cholDestroy */
+/* device-resident variants (no host round trip): d_elem has leading dimension ld >= nCol */
+int  hdsdpcu_linsys_padded_dim(void *chol);                   /* leading dimension of the internal buffers */
+int  hdsdpcu_linsys_numeric_dev(void *chol, const double *d_elem, long ld, int *info);
+int  hdsdpcu_linsys_solve_dev(void *chol, int nRhs, double *d_x, long ldx);           /* in place, ldx >= padded dim, padding zero */
+int  hdsdpcu_linsys_invert_dev(void *chol, double *d_inv);    /* padded_dim x padded_dim, full symmetric */
+double *hdsdpcu_linsys_factor_dev(void *chol);                /* device pointer of L (ld = padded dim) */
+
+/* ---------------------------------------------------------------------------------------------
+ * B2 -- SDP cone.  Replaces the hot-path members of the cone vtable (reference
+ * interface/def_hdsdp_conic.h:56-107) for hdsdp_cone_sdp_dense / hdsdp_cone_sdp_sparse:
+ *   create          = coneProcData + conePresolveData   hdsdp_conic_sdp.c:1356-1400, :1490-1518
+ *                     (user_data CSC [n(n+1)/2 x (m+1)], column 0 = objective, def_hdsdp_user_data.h:22-32)
+ *   setstart        = coneSetStart      :1546        reduceresi = coneReduceResi :2226
+ *   setperturb      = coneSetPerturb    :2238        scal       = coneScal       :1604
+ *   update          = coneUpdate        :1616   S = -Rd I - A'y + tau C  into BUFFER_DUALVAR
+ *   updatebuffer    = sdpDenseConeIUpdateBuffer :343 (generic linear combination, any buffer)
+ *   interiorcheck   = coneInteriorCheck :2172   (update + Cholesky, *isInterior = PSD)
+ *   interiorcheckexpert = coneInteriorCheckExpert :2192
+ *   getbarrier      = coneGetBarrier    :2252   (optional update + factor; logdet = 2 sum log L_ii)
+ *   addstepandcheck = coneAxpyBufferAndCheck :2333
+ *   buildschur      = coneBuildSchur    :1726 / :1814  (accumulates into the hdsdpcu kkt object)
+ * whichBuffer: 0 BUFFER_DUALVAR, 1 BUFFER_DUALCHECK, 2 BUFFER_DUALSTEP (interface/hdsdp_conic.h:24-26)
+ * typeKKT: 0 INFEASIBLE, 1 CORRECTOR, 2 HOMOGENEOUS, 3 PRIMAL (interface/hdsdp_conic.h:16-19)
+ * ------------------------------------------------------------------------------------------- */
+int  hdsdpcu_cone_create(void **pcone, int nRow, int nCol, const int *coneMatBeg, const int *coneMatIdx,
+                         const double *coneMatElem);
+void hdsdpcu_cone_destroy(void **pcone);
+int  hdsdpcu_cone_getdim(void *cone);
+int  hdsdpcu_cone_gettypes(void *cone, int *types /* nRow + 1, last = objective; sdp_coeff_type values */);
+void hdsdpcu_cone_setstart(void *cone, double rResi);
+void hdsdpcu_cone_reduceresi(void *cone, double resiReduction);
+void hdsdpcu_cone_setperturb(void *cone, double dDualPerturb);
+int  hdsdpcu_cone_scal(void *cone, double dScal);
+int  hdsdpcu_cone_update(void *cone, double barHsdTau, const double *rowDual);
+int  hdsdpcu_cone_update_dev(void *cone, double barHsdTau, const double *d_rowDual);
+int  hdsdpcu_cone_updatebuffer(void *cone, double dCCoef, double dACoefScal, const double *dACoef, double dEyeCoef,
+                               int whichBuffer);
+int  hdsdpcu_cone_interiorcheck(void *cone, double barHsdTau, const double *rowDual, int *isInterior);
+int  hdsdpcu_cone_interiorcheckexpert(void *cone, double dCCoef, double dACoefScal, const double *dACoef,
+                                      double dEyeCoef, int whichBuffer, int *isInterior);
+int  hdsdpcu_cone_factorize(void *cone, int whichBuffer, int *isPsd);   /* HFpLinsysPsdCheck on the buffer */
+int  hdsdpcu_cone_getbarrier(void *cone, double barHsdTau, const double *rowDual /* may be NULL */, int whichBuffer,
+                             double *logdet);
+int  hdsdpcu_cone_addstepandcheck(void *cone, double dStep, int whichBuffer, int *isInterior);
+int  hdsdpcu_cone_buildschur(void *cone, int iCone, void *kkt, int typeKKT);
+/* test / debug mirrors (D2H): n x n column-major */
+int  hdsdpcu_cone_getbuffer(void *cone, int whichBuffer, double *out);
+int  hdsdpcu_cone_getsinv(void *cone, double *out);
+int  hdsdpcu_cone_getfactordiag(void *cone, int whichBuffer, double *diag);
+
+/* ---------------------------------------------------------------------------------------------
+ * B2 -- Schur complement object.  Replaces hdsdp_kkt (reference interface/def_hdsdp_schur.h:32-68)
+ * for the dense-M case and the HKKT* calls of interface/hdsdp_schur.c:
+ *   create (+addcone) = HKKTCreate + HKKTInit :170-254     buildup   = HKKTBuildUp :256
+ *   buildupextra_*    = HKKTBuildUpExtraCone :270 for the bound cone (hdsdp_conic_bound.c:201-249)
+ *                       and the LP cone (hdsdp_conic_lp.c:254-330)
+ *   regularize = HKKTRegularize :348    export = HKKTExport :293    factorize = HKKTFactorize :328
+ *   solve      = HKKTSolve :338 (direct Cholesky instead of PCG)    registerpsdp = HKKTRegisterPSDP :375
+ * M (m x m, lower) lives in HBM from clean to the last solve; getmatrix is a test-only mirror.
+ * ------------------------------------------------------------------------------------------- */
+int  hdsdpcu_kkt_create(void **pkkt, int nRow);
+int  hdsdpcu_kkt_addcone(void *kkt, void *cone);
+void hdsdpcu_kkt_destroy(void **pkkt);
+int  hdsdpcu_kkt_buildup(void *kkt, int typeKKT);
+int  hdsdpcu_kkt_clean(void *kkt, int typeKKT);
+int  hdsdpcu_kkt_buildupextra_bound(void *kkt, const double *diagAdd, const double *asinvAdd, const double *asinvRdAdd,
+                                    int typeKKT);
+int  hdsdpcu_lp_create(void **plp, int nRow, int nLpCol, const int *matBeg, const int *matIdx, const double *matElem);
+void hdsdpcu_lp_destroy(void **plp);
+int  hdsdpcu_kkt_buildupextra_lp(void *kkt, void *lp, const double *colDualInverse, double dualResidual, int typeKKT);
+int  hdsdpcu_kkt_regularize(void *kkt, double dKKTReg);
+int  hdsdpcu_kkt_export(void *kkt, double *dASinvVec, double *dASinvRdSinvVec, double *dASinvCSinvVec,
+                        double *dCSinvCSinv, double *dCSinv, double *dCSinvRdSinv, double *dTraceSinv);
+int  hdsdpcu_kkt_factorize(void *kkt);
+int  hdsdpcu_kkt_solve(void *kkt, const double *dRhsVec, double *dLhsVec /* NULL: in place */);
+int  hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *dRhsVec, double *dLhsVec);
+void hdsdpcu_kkt_registerpsdp(void *kkt, double **dPrimalX);
+int  hdsdpcu_kkt_getmatrix(void *kkt, double *M /* nRow x nRow column-major, lower meaningful */);
+/* device-resident variants used by bench.py's HBM-resident timing */
+int     hdsdpcu_kkt_padded_dim(void *kkt);
+double *hdsdpcu_kkt_matrix_dev(void *kkt);
+double *hdsdpcu_kkt_asinv_dev(void *kkt);
+int     hdsdpcu_kkt_solve_dev(void *kkt, int nRhs, double *d_x /* stride padded dim, padding zero, in place */);
+/* multi-GPU: this process builds only Schur columns j with (j / 128) % nRanks == rank */
+int  hdsdpcu_kkt_setshard(void *kkt, int rank, int nRanks);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone kernels exposed for tests and roofline measurement
+ * ------------------------------------------------------------------------------------------- */
+/* C (M x N) = alpha A (M x K) B(N x K)^T + beta C on device pointers; M,N % 128 == 0, K % 16 == 0 */
+int hdsdpcu_dgemm_nt_dev(int M, int N, int K, double alpha, const double *dA, long lda, const double *dB, long ldb,
+                         double beta, double *dC, long ldc, int lowerOnly);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDSDPCU_H */

@@ -1,0 +1,94 @@
+"""GPU parity of the dense linear-system back-end (B1) against numpy/LAPACK on the same inputs.
+
+Floating point: tolerance 1e-10 relative (BASELINE.json north_star) on factor diagonal, inverse and solves
+for well-conditioned SPD inputs; PSD detection must agree exactly.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def spd(n, seed, cond=1e3):
+    rs = np.random.RandomState(seed)
+    Q, _ = np.linalg.qr(rs.standard_normal((n, n)))
+    ev = np.logspace(0, np.log10(cond), n)
+    return (Q * ev) @ Q.T
+
+
+@pytest.mark.parametrize("n", [1, 7, 100, 128, 129, 300, 1000])
+def test_factor_diag_inverse_solve(n):
+    from hdsdp_b200.api import DenseLinsys
+    A = spd(n, n)
+    A = 0.5 * (A + A.T)
+    ls = DenseLinsys(n)
+    Ain = np.asfortranarray(np.tril(A) + np.triu(np.full((n, n), 7.5), 1))  # garbage strict upper: must be ignored
+    keep = Ain.copy()
+    assert ls.numeric(Ain) == 0
+    assert np.array_equal(Ain, keep), "HFpLinsysNumeric must not modify the caller's matrix"
+    L = np.linalg.cholesky(A)
+    np.testing.assert_allclose(ls.get_diag(), np.diag(L), rtol=1e-10)
+    inv = ls.invert()
+    ref = np.linalg.inv(A)
+    assert np.abs(inv - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert np.abs(inv - inv.T).max() == 0.0, "inverse must be exactly symmetric (mirrored lower)"
+    rs = np.random.RandomState(1)
+    b = rs.standard_normal(n)
+    x = ls.solve(b)
+    assert np.abs(x - np.linalg.solve(A, b)).max() <= 1e-9 * np.abs(x).max()
+    f = ls.fsolve(b)
+    assert np.abs(f - np.linalg.solve(L, b)).max() <= 1e-10 * max(1.0, np.abs(f).max())
+    g = ls.bsolve(b)
+    assert np.abs(g - np.linalg.solve(L.T, b)).max() <= 1e-10 * max(1.0, np.abs(g).max())
+    B = rs.standard_normal((n, 3))
+    X = ls.solve(B)
+    assert np.abs(X - np.linalg.solve(A, B)).max() <= 1e-9 * np.abs(X).max()
+    ls.close()
+
+
+@pytest.mark.parametrize("n,bad", [(5, 2), (200, 150), (300, 299), (260, 0)])
+def test_not_positive_definite(n, bad):
+    from hdsdp_b200.api import DenseLinsys
+    A = spd(n, 3)
+    A[bad, bad] = -1.0
+    ls = DenseLinsys(n)
+    assert ls.psd_check(A) is False
+    assert ls.numeric(A) == 1  # HDSDP_RETCODE_FAILED where dpotrf reports info > 0
+    assert ls.psd_check(spd(n, 4)) is True
+    ls.close()
+
+
+def test_gemm_nt_matches_numpy():
+    import torch
+    from hdsdp_b200 import _lib
+    lib = _lib.require_gpu()
+    M, N, K = 256, 384, 144
+    rs = np.random.RandomState(0)
+    A = rs.standard_normal((M, K)); B = rs.standard_normal((N, K)); C = rs.standard_normal((M, N))
+    dA = torch.tensor(A.T.copy(), device="cuda")  # column-major M x K == row-major K x M
+    dB = torch.tensor(B.T.copy(), device="cuda")
+    dC = torch.tensor(C.T.copy(), device="cuda")
+    torch.cuda.synchronize()
+    rc = lib.hdsdpcu_dgemm_nt_dev(M, N, K, -1.5, dA.data_ptr(), M, dB.data_ptr(), N, 0.5, dC.data_ptr(), M, 0)
+    assert rc == 0
+    lib.hdsdpcu_sync()
+    got = dC.cpu().numpy().T
+    ref = -1.5 * A @ B.T + 0.5 * C
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max() * K
+
+
+def test_large_factor_residual():
+    """n = 4096: relative residual |A - L L^T| through solves, and log det against numpy."""
+    from hdsdp_b200.api import DenseLinsys
+    n = 4096
+    rs = np.random.RandomState(5)
+    G = rs.standard_normal((n, n // 2))
+    A = G @ G.T + n * np.eye(n)
+    ls = DenseLinsys(n)
+    assert ls.numeric(A) == 0
+    b = rs.standard_normal(n)
+    x = ls.solve(b)
+    assert np.abs(A @ x - b).max() <= 1e-10 * np.abs(b).max() * 10
+    sign, ld = np.linalg.slogdet(A)
+    assert abs(2 * np.log(ls.get_diag()).sum() - ld) <= 1e-10 * abs(ld)
+    ls.close()
