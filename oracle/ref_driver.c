@@ -219,9 +219,16 @@ int refdrv_get_classification(refdrv *h, int k, int *types, int *perm, int *stra
 
 /* rank-one sign (scale) of row i of dense-type cone k after presolve; 0 if not rank one */
 double refdrv_get_r1_sign(refdrv *h, int k, int i) {
-    if (h->cones[k]->cone != HDSDP_CONETYPE_DENSE_SDP) return 0.0;
-    hdsdp_cone_sdp_dense *c = (hdsdp_cone_sdp_dense *) h->cones[k]->coneData;
-    sdp_coeff *a = (i < h->nRows) ? c->sdpRow[i] : c->sdpObj;
+    sdp_coeff *a = NULL;
+    if (h->cones[k]->cone == HDSDP_CONETYPE_DENSE_SDP) {
+        hdsdp_cone_sdp_dense *c = (hdsdp_cone_sdp_dense *) h->cones[k]->coneData;
+        a = (i < h->nRows) ? c->sdpRow[i] : c->sdpObj;
+    } else if (h->cones[k]->cone == HDSDP_CONETYPE_SPARSE_SDP) {
+        hdsdp_cone_sdp_sparse *c = (hdsdp_cone_sdp_sparse *) h->cones[k]->coneData;
+        if (i >= h->nRows) a = c->sdpObj;
+        else for (int e = 0; e < c->nRowElem; ++e) if (c->rowIdx[e] == i) a = c->sdpRow[e];
+    }
+    if (!a) return 0.0;
     if (a->dataType == SDP_COEFF_SPR1) return ((sdp_coeff_spr1 *) a->dataMat)->spR1FactorSign;
     if (a->dataType == SDP_COEFF_DSR1) return ((sdp_coeff_dsr1 *) a->dataMat)->r1FactorSign;
     return 0.0;

