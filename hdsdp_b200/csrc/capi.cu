@@ -63,6 +63,12 @@ long hdsdpcu_launch_count(int reset) {
     return v;
 }
 
+int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes) {
+    HD_CALL(ensure_ready());
+    HD_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t) bytes, cudaMemcpyDeviceToDevice, g_stream));
+    return HD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // B1: dense linear system back-end
 // ------------------------------------------------------------------------------------------------

@@ -29,6 +29,8 @@ int hdsdpcu_sync(void);
 const char *hdsdpcu_version(void);
 /* count of kernel launches issued by this library since the last reset (bench.py "gpu_launches") */
 long hdsdpcu_launch_count(int reset);
+/* device-to-device copy on the library stream (bench plumbing for HBM-resident inputs) */
+int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes);
 
 /* ---------------------------------------------------------------------------------------------
  * B1 -- dense linear-system back-end.  One-for-one replacement of the 11 function pointers of
