@@ -193,7 +193,7 @@ def run_ours(args):
     setup_s = time.time() - t0
     mp = lib.hdsdpcu_kkt_padded_dim(kkt.h)
 
-    peak = cublas_dgemm_peak(torch) if rank == 0 else 0.0
+    peak = cublas_dgemm_peak(torch) if (rank == 0 and not args.no_peak) else 0.0
 
     # device-resident inputs for `value`: y per step and the two right-hand sides (b and A S^-1)
     nsteps = args.warmup + args.steps
@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--n", type=int, default=THETA_N)
     ap.add_argument("--edges", type=int, default=THETA_EDGES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peak", action="store_true", help="skip the live cuBLAS DGEMM peak measurement (ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
