@@ -64,6 +64,8 @@ _SIGNATURES = {
     "hdsdpcu_cone_getbarrier": (c_int, [c_void_p, c_double, c_double_p, c_int, c_double_p]),
     "hdsdpcu_cone_addstepandcheck": (c_int, [c_void_p, c_double, c_int, c_int_p]),
     "hdsdpcu_cone_buildschur": (c_int, [c_void_p, c_int, c_void_p, c_int]),
+    "hdsdpcu_cone_setsinv": (c_int, [c_void_p, c_double_p]),
+    "hdsdpcu_cone_setsinv_linsys": (c_int, [c_void_p, c_void_p]),
     "hdsdpcu_cone_getbuffer": (c_int, [c_void_p, c_int, c_double_p]),
     "hdsdpcu_cone_getsinv": (c_int, [c_void_p, c_double_p]),
     "hdsdpcu_cone_getfactordiag": (c_int, [c_void_p, c_int, c_double_p]),
@@ -82,7 +84,8 @@ _SIGNATURES = {
     "hdsdpcu_kkt_factorize": (c_int, [c_void_p]),
     "hdsdpcu_kkt_solve": (c_int, [c_void_p, c_double_p, c_double_p]),
     "hdsdpcu_kkt_solve_many": (c_int, [c_void_p, c_int, c_double_p, c_double_p]),
-    "hdsdpcu_kkt_registerpsdp": (None, [c_void_p, POINTER(c_double_p)]),
+    "hdsdpcu_kkt_registerpsdp": (None, [c_void_p, c_int, POINTER(c_double_p)]),
+    "hdsdpcu_kkt_addhost": (c_int, [c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "hdsdpcu_kkt_getmatrix": (c_int, [c_void_p, c_double_p]),
     "hdsdpcu_kkt_padded_dim": (c_int, [c_void_p]),
     "hdsdpcu_kkt_matrix_dev": (c_void_p, [c_void_p]),

@@ -293,7 +293,7 @@ class KKT:
         self._primal_keep = [np.asfortranarray(X, dtype=np.float64) for X in Xs]
         arr = (c_double_p * len(Xs))(*[_dp(X) for X in self._primal_keep])
         self._primal_arr = arr
-        self.lib.hdsdpcu_kkt_registerpsdp(self.h, arr)
+        self.lib.hdsdpcu_kkt_registerpsdp(self.h, len(Xs), arr)
 
     def get_matrix(self) -> np.ndarray:
         M = np.zeros((self.m, self.m), order="F")

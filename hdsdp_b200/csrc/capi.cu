@@ -328,6 +328,24 @@ int hdsdpcu_cone_buildschur(void *cone, int iCone, void *kkt, int typeKKT) {
     return cone_build_schur((ConeCU *) cone, iCone, (KktCU *) kkt, typeKKT);
 }
 
+int hdsdpcu_cone_setsinv(void *cone, const double *fullInv) {
+    ConeCU *c = (ConeCU *) cone;
+    HD_CUDA(cudaMemsetAsync(c->d_sinv, 0, sizeof(double) * (size_t) c->np * c->np, g_stream));
+    HD_CUDA(cudaMemcpy2DAsync(c->d_sinv, (size_t) c->np * 8, fullInv, (size_t) c->n * 8, (size_t) c->n * 8, c->n,
+                              cudaMemcpyHostToDevice, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    c->sinv_valid = true;
+    return HD_OK;
+}
+int hdsdpcu_cone_setsinv_linsys(void *cone, void *chol) {
+    ConeCU *c = (ConeCU *) cone;
+    LinsysCU *l = (LinsysCU *) chol;
+    if (!l || l->c->np != c->np || !l->c->factored) return HD_FAILED;
+    HD_CALL(chol_invert(g_stream, l->c, c->d_sinv));
+    c->sinv_valid = true;
+    return HD_OK;
+}
+
 int hdsdpcu_cone_getbuffer(void *cone, int which, double *out) {
     ConeCU *c = (ConeCU *) cone;
     HD_CUDA(cudaMemcpy2DAsync(out, (size_t) c->n * 8, c->d_buf[which], (size_t) c->np * 8, (size_t) c->n * 8, c->n,
@@ -434,10 +452,13 @@ int hdsdpcu_kkt_export(void *kkt, double *a, double *ard, double *ac, double *cs
 int hdsdpcu_kkt_factorize(void *kkt) { return kkt_factorize((KktCU *) kkt, nullptr); }
 int hdsdpcu_kkt_solve(void *kkt, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, 1, rhs, lhs); }
 int hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, nRhs, rhs, lhs); }
-void hdsdpcu_kkt_registerpsdp(void *kkt, double **X) {
+void hdsdpcu_kkt_registerpsdp(void *kkt, int nCones, double **X) {
     KktCU *k = (KktCU *) kkt;
-    k->primalX.assign(k->cones.size(), nullptr);
-    if (X) for (size_t i = 0; i < k->cones.size(); ++i) k->primalX[i] = X[i];
+    k->primalX.assign(nCones > 0 ? nCones : 0, nullptr);
+    if (X) for (int i = 0; i < nCones; ++i) k->primalX[i] = X[i];
+}
+int hdsdpcu_kkt_addhost(void *kkt, const double *d, const double *a, const double *ard, const double *ac, const double *s4) {
+    return kkt_add_host((KktCU *) kkt, d, a, ard, ac, s4);
 }
 int hdsdpcu_kkt_getmatrix(void *kkt, double *M) { return kkt_get_matrix((KktCU *) kkt, M); }
 int hdsdpcu_kkt_padded_dim(void *kkt) { return ((KktCU *) kkt)->mp; }

@@ -100,6 +100,11 @@ int  hdsdpcu_cone_getbarrier(void *cone, double barHsdTau, const double *rowDual
                              double *logdet);
 int  hdsdpcu_cone_addstepandcheck(void *cone, double dStep, int whichBuffer, int *isInterior);
 int  hdsdpcu_cone_buildschur(void *cone, int iCone, void *kkt, int typeKKT);
+/* Hand the cone an S^-1 computed elsewhere (used by the integration shim, whose S factor is owned by the
+ * reference's hdsdp_linsys_fp): from a host n x n matrix, or device-to-device from a hdsdpcu_linsys handle
+ * (HFpLinsysInvert, linalg/hdsdp_linsolver.c:2120, without the host round trip).  Valid until the next update. */
+int  hdsdpcu_cone_setsinv(void *cone, const double *fullInv);
+int  hdsdpcu_cone_setsinv_linsys(void *cone, void *chol);
 /* test / debug mirrors (D2H): n x n column-major */
 int  hdsdpcu_cone_getbuffer(void *cone, int whichBuffer, double *out);
 int  hdsdpcu_cone_getsinv(void *cone, double *out);
@@ -122,6 +127,10 @@ int  hdsdpcu_kkt_buildup(void *kkt, int typeKKT);
 int  hdsdpcu_kkt_clean(void *kkt, int typeKKT);
 int  hdsdpcu_kkt_buildupextra_bound(void *kkt, const double *diagAdd, const double *asinvAdd, const double *asinvRdAdd,
                                     int typeKKT);
+/* generic host-computed increments (any pointer may be NULL): diag(M), dASinvVec, dASinvRdSinvVec, dASinvCSinvVec,
+ * scalars {dCSinvCSinv, dCSinv, dCSinvRdSinv, dTraceSinv} */
+int  hdsdpcu_kkt_addhost(void *kkt, const double *diagAdd, const double *asinvAdd, const double *asinvRdAdd,
+                         const double *asinvCAdd, const double *scalarsAdd4);
 int  hdsdpcu_lp_create(void **plp, int nRow, int nLpCol, const int *matBeg, const int *matIdx, const double *matElem);
 void hdsdpcu_lp_destroy(void **plp);
 int  hdsdpcu_kkt_buildupextra_lp(void *kkt, void *lp, const double *colDualInverse, double dualResidual, int typeKKT);
@@ -131,7 +140,7 @@ int  hdsdpcu_kkt_export(void *kkt, double *dASinvVec, double *dASinvRdSinvVec, d
 int  hdsdpcu_kkt_factorize(void *kkt);
 int  hdsdpcu_kkt_solve(void *kkt, const double *dRhsVec, double *dLhsVec /* NULL: in place */);
 int  hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *dRhsVec, double *dLhsVec);
-void hdsdpcu_kkt_registerpsdp(void *kkt, double **dPrimalX);
+void hdsdpcu_kkt_registerpsdp(void *kkt, int nCones, double **dPrimalX);
 int  hdsdpcu_kkt_getmatrix(void *kkt, double *M /* nRow x nRow column-major, lower meaningful */);
 /* device-resident variants used by bench.py's HBM-resident timing */
 int     hdsdpcu_kkt_padded_dim(void *kkt);

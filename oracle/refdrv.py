@@ -12,7 +12,9 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_void_p
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_LIB = os.path.join(_HERE, "_ref", "libhdsdp_ref.so")
+# HDSDP_REFDRV_LIB selects another build exposing the same driver entry points (the integration build
+# integration/_build/libhdsdp_integrated.so = unmodified reference host + CUDA hot path); one library per process.
+REF_LIB = os.environ.get("HDSDP_REFDRV_LIB") or os.path.join(_HERE, "_ref", "libhdsdp_ref.so")
 c_double_p = POINTER(c_double)
 c_int_p = POINTER(c_int)
 

@@ -1,0 +1,57 @@
+"""End-to-end drop-in parity: the UNMODIFIED reference IPM driver (interface/hdsdp.c, hdsdp_algo.c, ...) linked against
+the CUDA hot path through integration/hdsdp_schur_cuda.c + integration/hdsdp_linsys_cuda.c
+(integration/_build/libhdsdp_integrated.so, built by integration/build_integrated.sh where /root/reference exists)
+must reproduce the CPU reference's full solves recorded in the golden fixtures.
+
+Gates (BASELINE.json north_star): primal/dual objectives within 1e-7 relative, same IPM iteration count within +-1.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+
+INTEGRATED = os.path.join(ROOT, "integration", "_build", "libhdsdp_integrated.so")
+
+HELPER = r"""
+import json, sys
+sys.path.insert(0, {root!r})
+sys.path.insert(0, {tests!r})
+from conftest import load_golden
+from oracle import refdrv
+prob, z = load_golden({name!r})
+res = refdrv.optimize(prob)
+print("RESULT " + json.dumps({{"pObj": res["pObj"], "dObj": res["dObj"], "iterations": res["iterations"], "status": res["status"],
+                              "retcode": res["retcode"], "dimacs": list(res["dimacs"])}}))
+"""
+
+
+def solve_integrated(name):
+    env = dict(os.environ, HDSDP_REFDRV_LIB=INTEGRATED, OPENBLAS_NUM_THREADS="1")
+    code = HELPER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), name=name)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    for ln in out.stdout.splitlines():
+        if ln.startswith("RESULT "):
+            return json.loads(ln[7:]), out.stdout
+    raise AssertionError(f"integrated solve of {name} produced no result:\n{out.stdout[-3000:]}\n{out.stderr[-3000:]}")
+
+
+@pytest.mark.parametrize("name", ["mcp100", "theta1", "truss1", "gpp100", "maxcut40", "theta30"])
+def test_full_solve_matches_cpu_reference(name):
+    if not os.path.exists(INTEGRATED):
+        pytest.skip("integration/_build/libhdsdp_integrated.so not built (needs /root/reference at build time)")
+    _, z = load_golden(name)
+    res, log = solve_integrated(name)
+    assert "libhdsdp_cuda" in log, "the integrated build must report that the GPU Schur path is in use"
+    ref_p, ref_d, ref_it = float(z["solve_pObj"]), float(z["solve_dObj"]), int(z["solve_iterations"])
+    assert res["retcode"] == 0 and res["status"] == int(z["solve_status"]), (res, int(z["solve_status"]))
+    assert abs(res["dObj"] - ref_d) <= 1e-7 * max(1.0, abs(ref_d)), f"dObj {res['dObj']!r} vs CPU reference {ref_d!r}"
+    assert abs(res["pObj"] - ref_p) <= 1e-7 * max(1.0, abs(ref_p)), f"pObj {res['pObj']!r} vs CPU reference {ref_p!r}"
+    assert abs(res["iterations"] - ref_it) <= 1, f"iterations {res['iterations']} vs CPU reference {ref_it}"
+    assert max(res["dimacs"]) <= 1e-2     # the reference's own acceptance gate (interface/hdsdp.c:905-922)
