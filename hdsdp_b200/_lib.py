@@ -29,6 +29,7 @@ _SIGNATURES = {
     "hdsdpcu_version": (c_char_p, []),
     "hdsdpcu_launch_count": (c_long, [c_int]),
     "hdsdpcu_copy_dev": (c_int, [c_void_p, c_void_p, c_long]),
+    "hdsdpcu_set_option": (c_int, [c_char_p, c_int]),
     # B1
     "hdsdpcu_linsys_create": (c_int, [POINTER(c_void_p), c_int]),
     "hdsdpcu_linsys_setparam": (None, [c_void_p, c_void_p]),

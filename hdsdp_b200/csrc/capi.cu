@@ -63,6 +63,14 @@ long hdsdpcu_launch_count(int reset) {
     return v;
 }
 
+void hd_gemm_set_variant(int v);
+}
+extern "C" {
+int hdsdpcu_set_option(const char *name, int value) {
+    if (name && strcmp(name, "gemm_variant") == 0) { hd_gemm_set_variant(value); return HD_OK; }
+    return HD_FAILED;
+}
+
 int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes) {
     HD_CALL(ensure_ready());
     HD_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t) bytes, cudaMemcpyDeviceToDevice, g_stream));

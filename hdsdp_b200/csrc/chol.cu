@@ -97,76 +97,16 @@ __global__ void leaf_transpose_kernel(const double *__restrict__ Dinv, double *X
     for (int r = ty; r < 32; r += 8) X[(long) (bx + r) * ldx + by + tx] = t[tx][r]; // X[k, i] = Dinv[i, k]
 }
 
-// ------------------------------------------------------------------------------------------
-// GEMV helpers for the vector triangular solves (HBM-bound; algorithmic bytes = 8 per entry of L)
-// ------------------------------------------------------------------------------------------
-constexpr int GV_COLS = 256;
-
-// y[rows] -= A[rows x cols] * x[cols]     grid (rows/128, ceil(cols/GV_COLS)), 128 threads
-__global__ void __launch_bounds__(128) gemv_n_sub_kernel(const double *__restrict__ A, long lda, int cols,
-                                                        const double *x, double *y) {
-    __shared__ double xs[GV_COLS];
-    const int c0 = blockIdx.y * GV_COLS;
-    const int nc = min(GV_COLS, cols - c0);
-    for (int c = threadIdx.x; c < nc; c += 128) xs[c] = x[c0 + c];
+// transposed copies of every inverse leaf (coalesced access for the L^T solve), one CTA per leaf
+__global__ void leaf_transpose_all_kernel(const double *__restrict__ Dinv, double *DinvT) {
+    __shared__ double t[32][33];
+    const double *src = Dinv + (long) blockIdx.z * HD_LEAF * HD_LEAF;
+    double *dst = DinvT + (long) blockIdx.z * HD_LEAF * HD_LEAF;
+    int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += 8) t[r][tx] = src[(long) (by + r) * HD_LEAF + bx + tx];
     __syncthreads();
-    const int r = blockIdx.x * 128 + threadIdx.x;
-    const double *a = A + (long) c0 * lda + r;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int c = 0;
-    for (; c + 4 <= nc; c += 4) {
-        s0 += a[(long) (c + 0) * lda] * xs[c + 0];
-        s1 += a[(long) (c + 1) * lda] * xs[c + 1];
-        s2 += a[(long) (c + 2) * lda] * xs[c + 2];
-        s3 += a[(long) (c + 3) * lda] * xs[c + 3];
-    }
-    for (; c < nc; ++c) s0 += a[(long) c * lda] * xs[c];
-    atomicAdd(&y[r], -((s0 + s1) + (s2 + s3)));
-}
-
-// y[cols] -= A[rows x cols]^T * x[rows]   grid (cols/128, ceil(rows/1024)), 256 threads (8 warps x 16 cols)
-constexpr int GT_ROWS = 1024;
-__global__ void __launch_bounds__(256) gemv_t_sub_kernel(const double *__restrict__ A, long lda, int rows,
-                                                        const double *x, double *y) {
-    __shared__ double xs[GT_ROWS];
-    const int r0 = blockIdx.y * GT_ROWS;
-    const int nr = min(GT_ROWS, rows - r0);
-    for (int r = threadIdx.x; r < nr; r += 256) xs[r] = x[r0 + r];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int cc = 0; cc < 16; ++cc) {
-        const int c = blockIdx.x * 128 + warp * 16 + cc;
-        const double *a = A + (long) c * lda + r0;
-        double s = 0.0;
-        for (int r = lane; r < nr; r += 32) s += a[r] * xs[r];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) atomicAdd(&y[c], -s);
-    }
-}
-
-// x[128] <- Dinv * x  (trans == 0)  or  Dinv^T * x (trans == 1);  one CTA of 128 threads per rhs
-__global__ void __launch_bounds__(128) leaf_solve_kernel(const double *__restrict__ Dinv, double *x, long ldx, int trans) {
-    __shared__ double xs[HD_LEAF];
-    double *xv = x + (long) blockIdx.x * ldx;
-    xs[threadIdx.x] = xv[threadIdx.x];
-    __syncthreads();
-    if (!trans) {
-        const int i = threadIdx.x;
-        double s = 0.0;
-        for (int k = 0; k <= i; ++k) s += Dinv[k * HD_LEAF + i] * xs[k];
-        xv[i] = s;
-    } else {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int ii = 0; ii < 32; ++ii) {
-            const int i = warp * 32 + ii; // out_i = sum_{k>=i} Dinv[k,i] x_k
-            double s = 0.0;
-            for (int k = i + lane; k < HD_LEAF; k += 32) s += Dinv[i * HD_LEAF + k] * xs[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) xv[i] = s;
-        }
-    }
+    for (int r = ty; r < 32; r += 8) dst[(long) (bx + r) * HD_LEAF + by + tx] = t[tx][r];
 }
 
 __global__ void logdet_kernel(const double *L, long ld, int n, double *out, double *diag) {
@@ -250,42 +190,6 @@ int invert_rec(cudaStream_t st, const double *L, long ldl, int n, const double *
     return trsm_rec(st, X + (long) n1 * ldx, ldx, n1, L + (long) n1 * ldl + n1, ldl, n2, dinv2);
 }
 
-// L x = b (in place), nrhs right-hand sides with stride ldx
-int fsolve_rec(cudaStream_t st, const double *L, long ldl, int n, const double *dinv, double *x, int nrhs, long ldx) {
-    if (n == HD_LEAF) {
-        HDK(leaf_solve_kernel)<<<nrhs, 128, 0, st>>>(dinv, x, ldx, 0);
-        HD_CUDA(cudaGetLastError());
-        return HD_OK;
-    }
-    int n1 = split_leaves(n), n2 = n - n1;
-    HD_CALL(fsolve_rec(st, L, ldl, n1, dinv, x, nrhs, ldx));
-    for (int r = 0; r < nrhs; ++r) {
-        dim3 grid(n2 / 128, (n1 + GV_COLS - 1) / GV_COLS);
-        HDK(gemv_n_sub_kernel)<<<grid, 128, 0, st>>>(L + n1, ldl, n1, x + r * ldx, x + r * ldx + n1);
-    }
-    HD_CUDA(cudaGetLastError());
-    return fsolve_rec(st, L + (long) n1 * ldl + n1, ldl, n2, dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF,
-                      x + n1, nrhs, ldx);
-}
-
-// L^T x = b (in place)
-int bsolve_rec(cudaStream_t st, const double *L, long ldl, int n, const double *dinv, double *x, int nrhs, long ldx) {
-    if (n == HD_LEAF) {
-        HDK(leaf_solve_kernel)<<<nrhs, 128, 0, st>>>(dinv, x, ldx, 1);
-        HD_CUDA(cudaGetLastError());
-        return HD_OK;
-    }
-    int n1 = split_leaves(n), n2 = n - n1;
-    HD_CALL(bsolve_rec(st, L + (long) n1 * ldl + n1, ldl, n2, dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF,
-                       x + n1, nrhs, ldx));
-    for (int r = 0; r < nrhs; ++r) {
-        dim3 grid(n1 / 128, (n2 + GT_ROWS - 1) / GT_ROWS);
-        HDK(gemv_t_sub_kernel)<<<grid, 256, 0, st>>>(L + n1, ldl, n2, x + r * ldx + n1, x + r * ldx);
-    }
-    HD_CUDA(cudaGetLastError());
-    return bsolve_rec(st, L, ldl, n1, dinv, x, nrhs, ldx);
-}
-
 } // namespace
 
 int chol_create(DenseChol **pc, int n) {
@@ -298,6 +202,10 @@ int chol_create(DenseChol **pc, int n) {
     if (cudaMalloc(&c->L, bytes) != cudaSuccess) { free(c); cudaGetLastError(); return HD_MEMORY; }
     if (cudaMalloc(&c->Dinv, (size_t) c->np * HD_LEAF * sizeof(double)) != cudaSuccess) {
         cudaFree(c->L); free(c); cudaGetLastError(); return HD_MEMORY;
+    }
+    if (cudaMalloc(&c->DinvT, (size_t) c->np * HD_LEAF * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&c->sync, sizeof(int) * (c->np / HD_LEAF + 2)) != cudaSuccess) {
+        cudaFree(c->L); cudaFree(c->Dinv); free(c); cudaGetLastError(); return HD_MEMORY;
     }
     if (cudaMalloc(&c->dinfo, sizeof(int)) != cudaSuccess || cudaMallocHost(&c->hinfo, sizeof(int)) != cudaSuccess) {
         cudaFree(c->L); cudaFree(c->Dinv); free(c); cudaGetLastError(); return HD_MEMORY;
@@ -312,6 +220,8 @@ void chol_destroy(DenseChol *c) {
     if (!c) return;
     cudaFree(c->L);
     cudaFree(c->Dinv);
+    cudaFree(c->DinvT);
+    cudaFree(c->sync);
     cudaFree(c->dinfo);
     cudaFreeHost(c->hinfo);
     if (c->work) cudaFree(c->work);
@@ -338,6 +248,8 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     }
     HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
     HD_CALL(potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0));
+    HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);
+    HD_CUDA(cudaGetLastError());
     HD_CUDA(cudaMemcpyAsync(c->hinfo, c->dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
     HD_CUDA(cudaStreamSynchronize(st));
     int inf = *c->hinfo;
@@ -361,10 +273,10 @@ int chol_invert(cudaStream_t st, DenseChol *c, double *inv) {
 }
 
 int chol_fsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx) {
-    return fsolve_rec(st, c->L, c->np, c->np, c->Dinv, x, nrhs, ldx);
+    return hd_trsv(st, false, c->L, c->np, c->Dinv, c->DinvT, c->np, x, nrhs, ldx, c->sync);
 }
 int chol_bsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx) {
-    return bsolve_rec(st, c->L, c->np, c->np, c->Dinv, x, nrhs, ldx);
+    return hd_trsv(st, true, c->L, c->np, c->Dinv, c->DinvT, c->np, x, nrhs, ldx, c->sync);
 }
 
 int chol_logdet(cudaStream_t st, DenseChol *c, double *dlogdet, double *ddiag) {

@@ -79,6 +79,8 @@ struct DenseChol {
     int np;       // padded dimension (multiple of 128) == leading dimension
     double *L;    // np x np factor (lower); strict upper of diagonal leaves is garbage
     double *Dinv; // (np/128) inverse leaves, each 128 x 128 column-major lower triangular
+    double *DinvT; // their transposes (for the L^T solve)
+    int *sync;    // ticket + ready flags of the one-launch triangular solves
     int *dinfo;   // device: 0 ok, else 1-based index of the first non-positive pivot
     int *hinfo;   // pinned host mirror
     double *work; // np x np workspace (inverse / staging), allocated lazily
@@ -98,6 +100,8 @@ int chol_invert(cudaStream_t st, DenseChol *c, double *inv);
 int chol_fsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx);
 int chol_bsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx);
 // sum_i log(L_ii) * 2 written to *dlogdet (device) ; diag(L) to ddiag (device, n) if non-null
+int hd_trsv(cudaStream_t st, bool transposed, const double *L, long ldl, const double *Dinv, const double *DinvT, int np,
+            double *x, int nrhs, long ldx, int *sync);
 int chol_logdet(cudaStream_t st, DenseChol *c, double *dlogdet, double *ddiag);
 
 // small utility kernels (util.cu)

@@ -21,10 +21,8 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 128;
 constexpr int LDS_ = 132;                    // padded smem row stride (doubles)
-constexpr int STAGE_DOUBLES = 2 * BK * LDS_; // A tile + B tile
-constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
 constexpr int GROUP = 8;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -69,7 +67,9 @@ __device__ __forceinline__ bool map_tile(const TileMap &tmap, int bid, int &tm, 
     return true;
 }
 
+template <int BK, int STAGES>
 __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
+    constexpr int STAGE_DOUBLES = 2 * BK * LDS_; // A tile + B tile
     extern __shared__ __align__(16) double smem[];
     int tm, tn;
     if (!map_tile(tmap, blockIdx.x, tm, tn)) return;
@@ -88,20 +88,20 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tm
     const double *Ag = g.A + (long) k_lo * g.lda + m0;
     const double *Bg = g.B + (long) k_lo * g.ldb + n0;
 
-    // cp.async mapping: each operand stage = 16 k-rows x 128 doubles = 1024 16-byte chunks
+    // cp.async mapping: each operand stage = BK k-rows x 128 doubles = BK*64 16-byte chunks
     auto load_stage = [&](int stage, int kt) {
         double *As = smem + stage * STAGE_DOUBLES;
         double *Bs = As + BK * LDS_;
         const double *a = Ag + (long) kt * BK * g.lda;
         const double *b = Bg + (long) kt * BK * g.ldb;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < BK / 4; ++i) {
             int c = tid + i * 256;
             int kr = c >> 6, mc = (c & 63) * 2;
             cp_async16(As + kr * LDS_ + mc, a + (long) kr * g.lda + mc);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < BK / 4; ++i) {
             int c = tid + i * 256;
             int kr = c >> 6, nc = (c & 63) * 2;
             cp_async16(Bs + kr * LDS_ + nc, b + (long) kr * g.ldb + nc);
@@ -182,8 +182,13 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tm
 
 int g_num_sms = 0;
 bool g_attr_set = false;
+int g_variant = 1; // 0: BK=16 x 4 stages, 1: BK=32 x 3 stages
+
+template <int BK, int STAGES> constexpr int smem_bytes() { return STAGES * 2 * BK * LDS_ * 8; }
 
 } // namespace
+
+void hd_gemm_set_variant(int v) { g_variant = v; }
 
 int hd_num_sms() {
     if (g_num_sms == 0) {
@@ -197,12 +202,13 @@ int hd_num_sms() {
 
 int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
     if (g.M <= 0 || g.N <= 0) return HD_OK;
-    if (g.M % BM || g.N % BN || g.K % BK) {
+    if (g.M % BM || g.N % BN || g.K % 32) {
         fprintf(stderr, "[hdsdpcu] gemm_nt: unpadded shape %d %d %d\n", g.M, g.N, g.K);
         return HD_FAILED;
     }
     if (!g_attr_set) {
-        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16, 4>()));
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<32, 3>()));
         g_attr_set = true;
     }
     TileMap tmap;
@@ -218,7 +224,9 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
         nsuper = (long) ((tmap.tiles_m + GROUP - 1) / GROUP) * ((tmap.tiles_n + GROUP - 1) / GROUP);
     }
     long nblocks = nsuper * GROUP * GROUP;
-    HDK(dgemm_nt_kernel)<<<(unsigned) nblocks, 256, SMEM_BYTES, st>>>(g, tmap);
+    ++g_hd_launches;
+    if (g_variant == 0) dgemm_nt_kernel<16, 4><<<(unsigned) nblocks, 256, smem_bytes<16, 4>(), st>>>(g, tmap);
+    else dgemm_nt_kernel<32, 3><<<(unsigned) nblocks, 256, smem_bytes<32, 3>(), st>>>(g, tmap);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
 }

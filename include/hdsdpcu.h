@@ -31,6 +31,8 @@ const char *hdsdpcu_version(void);
 long hdsdpcu_launch_count(int reset);
 /* device-to-device copy on the library stream (bench plumbing for HBM-resident inputs) */
 int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes);
+/* tuning knobs for measurements: "gemm_variant" 0 = 128x128x16 tile, 4 stages; 1 = 128x128x32 tile, 3 stages (default) */
+int hdsdpcu_set_option(const char *name, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * B1 -- dense linear-system back-end.  One-for-one replacement of the 11 function pointers of

@@ -62,7 +62,7 @@ def test_gemm_nt_matches_numpy():
     import torch
     from hdsdp_b200 import _lib
     lib = _lib.require_gpu()
-    M, N, K = 256, 384, 144
+    M, N, K = 256, 384, 160
     rs = np.random.RandomState(0)
     A = rs.standard_normal((M, K)); B = rs.standard_normal((N, K)); C = rs.standard_normal((M, N))
     dA = torch.tensor(A.T.copy(), device="cuda")  # column-major M x K == row-major K x M

@@ -62,14 +62,16 @@ def main():
     shapes = [(4096, 4096, 4096, 0), (8192, 8192, 8192, 0), (8192, 8192, 8192, 1), (16384, 16384, 2048, 1), (16384, 16384, 512, 1), (16384, 128, 128, 0)]
     if args.big:
         shapes += [(24576, 24576, 24576, 1)]
-    for (M, N, K, lower) in shapes:
+    for variant in (0, 1):
+      lib.hdsdpcu_set_option(b"gemm_variant", variant)
+      for (M, N, K, lower) in shapes:
         A = torch.randn(K, M, dtype=torch.float64, device="cuda"); B = torch.randn(K, N, dtype=torch.float64, device="cuda")
         C = torch.zeros(N, M, dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
         fn = lambda: lib.hdsdpcu_dgemm_nt_dev(M, N, K, 1.0, A.data_ptr(), M, B.data_ptr(), N, 0.0, C.data_ptr(), M, lower)
         best, mean = ev_time(st, fn, reps=3, warm=1)
         flops = 2.0 * M * N * K * (0.5 if lower else 1.0)
-        rec = {"probe": "dmma_gemm_nt", "M": M, "N": N, "K": K, "lower": lower, "ms": best * 1e3, "tflops_best": flops / best / 1e12, "tflops_mean": flops / mean / 1e12}
+        rec = {"probe": "dmma_gemm_nt", "variant": variant, "M": M, "N": N, "K": K, "lower": lower, "ms": best * 1e3, "tflops_best": flops / best / 1e12, "tflops_mean": flops / mean / 1e12}
         if M <= 4096:
             ref = (A.T @ B).T  # C^T layout: C is N x M row-major == M x N column-major
             rec["maxerr"] = float((C - ref).abs().max())
