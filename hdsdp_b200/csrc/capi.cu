@@ -63,9 +63,6 @@ long hdsdpcu_launch_count(int reset) {
     return v;
 }
 
-void hd_gemm_set_variant(int v);
-}
-extern "C" {
 int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "gemm_variant") == 0) { hd_gemm_set_variant(value); return HD_OK; }
     return HD_FAILED;

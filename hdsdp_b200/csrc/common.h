@@ -70,6 +70,7 @@ struct GemmArgs {
 
 int hd_gemm_nt(cudaStream_t st, const GemmArgs &g);
 int hd_num_sms();
+void hd_gemm_set_variant(int v);
 
 // ---------------------------------------------------------------------------------------------
 // Dense SPD factorisation object (device resident).
