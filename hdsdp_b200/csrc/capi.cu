@@ -65,6 +65,7 @@ long hdsdpcu_launch_count(int reset) {
 
 int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "gemm_variant") == 0) { hd_gemm_set_variant(value); return HD_OK; }
+    if (name && strcmp(name, "chol_block") == 0) { hd_chol_set_block(value); return HD_OK; }
     return HD_FAILED;
 }
 

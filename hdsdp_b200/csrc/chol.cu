@@ -241,13 +241,76 @@ int chol_load_dev(cudaStream_t st, DenseChol *c, const double *dS, long lds) {
     return HD_OK;
 }
 
+// Blocked right-looking Cholesky with one step of look-ahead (used for large matrices, i.e. the Schur matrix M).
+// The O(n^3) trailing update of step k (one lower-triangular DMMA GEMM with K = NB) runs on the main stream while a
+// second, high-priority stream factors the next diagonal block and solves the next panel (the recursive kernels
+// above: latency-bound leaves and thin GEMMs), so the low-efficiency panel work is hidden behind the big GEMM.
+//   main : [col k+1 -= P_k P_k^T] -> e_col ...... [trailing cols k+2.. -= P_k P_k^T (LOWER)] -> wait e_panel
+//   side :            wait e_col -> potrf(A_{k+1,k+1}) -> A_{k+2..,k+1} <- A L^-T -> e_panel
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_col = nullptr, g_ev_panel = nullptr;
+static int g_lookahead_nb = 1024; // block size; <= 0 disables the blocked path
+
+void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
+
+static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
+    if (!g_side) {
+        int lo = 0, hi = 0;
+        HD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        HD_CUDA(cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, hi));
+        HD_CUDA(cudaEventCreateWithFlags(&g_ev_col, cudaEventDisableTiming));
+        HD_CUDA(cudaEventCreateWithFlags(&g_ev_panel, cudaEventDisableTiming));
+    }
+    const int nblk = (np + NB - 1) / NB;
+    auto start = [&](int k) { return k * NB; };
+    auto size = [&](int k) { return (k == nblk - 1) ? np - k * NB : NB; };
+    auto leaves = [&](int k) { return dinv + (long) (start(k) / HD_LEAF) * HD_LEAF * HD_LEAF; };
+    // panel 0 on the main stream
+    HD_CALL(potrf_rec(st, A, lda, size(0), leaves(0), info, 0));
+    if (nblk > 1) HD_CALL(trsm_rec(st, A + size(0), lda, np - size(0), A, lda, size(0), leaves(0)));
+    for (int k = 0; k + 1 < nblk; ++k) {
+        const int s0 = start(k), b0 = size(k), s1 = start(k + 1), b1 = size(k + 1);
+        const double *P = A + s0 * lda; // panel k: rows s1.. are the solved block column
+        // (1) update block column k+1: diagonal block (lower tiles) and the rectangle below it
+        GemmArgs g{};
+        g.M = b1; g.N = b1; g.K = b0;
+        g.A = P + s1; g.lda = lda; g.B = P + s1; g.ldb = lda; g.C = A + (long) s1 * lda + s1; g.ldc = lda;
+        g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+        HD_CALL(hd_gemm_nt(st, g));
+        const int below = np - (s1 + b1);
+        if (below > 0) {
+            g.M = below; g.N = b1; g.flags = 0;
+            g.A = P + s1 + b1; g.C = A + (long) s1 * lda + s1 + b1;
+            HD_CALL(hd_gemm_nt(st, g));
+        }
+        HD_CUDA(cudaEventRecord(g_ev_col, st));
+        // (2) side stream: factor block k+1 and solve its panel
+        HD_CUDA(cudaStreamWaitEvent(g_side, g_ev_col, 0));
+        HD_CALL(potrf_rec(g_side, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1), info, s1));
+        if (below > 0) HD_CALL(trsm_rec(g_side, A + (long) s1 * lda + s1 + b1, lda, below, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1)));
+        HD_CUDA(cudaEventRecord(g_ev_panel, g_side));
+        // (3) main stream: the rest of the trailing matrix (columns of blocks k+2..)
+        if (below > 0) {
+            g.M = below; g.N = below; g.K = b0;
+            g.A = P + s1 + b1; g.B = P + s1 + b1; g.C = A + (long) (s1 + b1) * lda + s1 + b1;
+            g.flags = HD_GEMM_LOWER;
+            HD_CALL(hd_gemm_nt(st, g));
+        }
+        HD_CUDA(cudaStreamWaitEvent(st, g_ev_panel, 0));
+    }
+    return HD_OK;
+}
+
 int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     if (!g_leaf_attr) {
         HD_CUDA(cudaFuncSetAttribute(potf2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
         g_leaf_attr = true;
     }
     HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
-    HD_CALL(potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0));
+    if (g_lookahead_nb >= HD_LEAF && c->np >= 4 * g_lookahead_nb)
+        HD_CALL(potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (g_lookahead_nb / HD_LEAF) * HD_LEAF));
+    else
+        HD_CALL(potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0));
     HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);
     HD_CUDA(cudaGetLastError());
     HD_CUDA(cudaMemcpyAsync(c->hinfo, c->dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -71,6 +71,7 @@ struct GemmArgs {
 int hd_gemm_nt(cudaStream_t st, const GemmArgs &g);
 int hd_num_sms();
 void hd_gemm_set_variant(int v);
+void hd_chol_set_block(int nb);
 
 // ---------------------------------------------------------------------------------------------
 // Dense SPD factorisation object (device resident).

@@ -80,7 +80,8 @@ def main():
 
     # 3. Cholesky / inverse / solves through the linsys device entry points
     import ctypes
-    for n in (2048, 8192, 16384) + ((32768, 50000) if args.big else ()):
+    for n, blk in ((2048, 0), (8192, 0), (8192, 1024), (16384, 0), (16384, 1024), (16384, 2048)) + (((32768, 1024), (32768, 2048)) if args.big else ()):
+        lib.hdsdpcu_set_option(b"chol_block", blk)
         h = ctypes.c_void_p()
         assert lib.hdsdpcu_linsys_create(ctypes.byref(h), n) == 0
         npad = lib.hdsdpcu_linsys_padded_dim(h)
@@ -93,7 +94,7 @@ def main():
         t0 = time.time()
         fn = lambda: lib.hdsdpcu_linsys_numeric_dev(h, A.data_ptr(), n, ctypes.byref(info))
         best, mean = ev_time(st, fn, reps=2, warm=1)
-        rec = {"probe": "potrf", "n": n, "info": info.value, "ms": best * 1e3, "tflops": n ** 3 / 3.0 / best / 1e12}
+        rec = {"probe": "potrf", "n": n, "chol_block": blk, "info": info.value, "ms": best * 1e3, "tflops": n ** 3 / 3.0 / best / 1e12}
         # residual through one solve
         x = torch.zeros(npad, dtype=torch.float64, device="cuda"); b = torch.randn(n, dtype=torch.float64, device="cuda")
         x[:n] = b
@@ -103,7 +104,7 @@ def main():
         a0.record(st); fs(); a1.record(st); a1.synchronize()
         rec["solve_ms"] = a0.elapsed_time(a1)
         rec["solve_resid"] = float((A @ x[:n] - b).abs().max() / b.abs().max())
-        if n <= 16384:
+        if n <= 16384 and blk == 0:
             inv = torch.empty(npad * npad, dtype=torch.float64, device="cuda")
             fi = lambda: lib.hdsdpcu_linsys_invert_dev(h, inv.data_ptr())
             bi, _ = ev_time(st, fi, reps=2, warm=1)
