@@ -14,6 +14,7 @@
 // matrix size, so a whole factorisation can be captured into a CUDA graph by the caller.
 #include "common.h"
 #include <cmath>
+#include <vector>
 
 namespace {
 
@@ -262,12 +263,17 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
         HD_CUDA(cudaEventCreateWithFlags(&g_ev_panel, cudaEventDisableTiming));
     }
     const int nblk = (np + NB - 1) / NB;
+    const bool trace = getenv("HDSDPCU_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&]() { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     auto start = [&](int k) { return k * NB; };
     auto size = [&](int k) { return (k == nblk - 1) ? np - k * NB : NB; };
     auto leaves = [&](int k) { return dinv + (long) (start(k) / HD_LEAF) * HD_LEAF * HD_LEAF; };
     // panel 0 on the main stream
     HD_CALL(potrf_rec(st, A, lda, size(0), leaves(0), info, 0));
+    mark();
     if (nblk > 1) HD_CALL(trsm_rec(st, A + size(0), lda, np - size(0), A, lda, size(0), leaves(0)));
+    mark();
     for (int k = 0; k + 1 < nblk; ++k) {
         const int s0 = start(k), b0 = size(k), s1 = start(k + 1), b1 = size(k + 1);
         const double *P = A + s0 * lda; // panel k: rows s1.. are the solved block column
@@ -284,6 +290,7 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
             HD_CALL(hd_gemm_nt(st, g));
         }
         HD_CUDA(cudaEventRecord(g_ev_col, st));
+        mark();
         // (2) side stream: factor block k+1 and solve its panel
         HD_CUDA(cudaStreamWaitEvent(g_side, g_ev_col, 0));
         HD_CALL(potrf_rec(g_side, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1), info, s1));
@@ -296,7 +303,28 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
             g.flags = HD_GEMM_LOWER;
             HD_CALL(hd_gemm_nt(st, g));
         }
+        mark();
         HD_CUDA(cudaStreamWaitEvent(st, g_ev_panel, 0));
+        mark();
+    }
+    if (trace) {
+        cudaStreamSynchronize(st);
+        float t;
+        cudaEventElapsedTime(&t, tev[0], tev[1]);
+        fprintf(stderr, "[trace] potrf_blocked np=%d NB=%d panel0 trsm %.3f ms\n", np, NB, t);
+        double tc = 0, tg = 0, tw = 0;
+        for (int k = 0; k + 1 < nblk; ++k) {
+            float a, b, c;
+            cudaEventElapsedTime(&a, tev[1 + 3 * k], tev[2 + 3 * k]);
+            cudaEventElapsedTime(&b, tev[2 + 3 * k], tev[3 + 3 * k]);
+            cudaEventElapsedTime(&c, tev[3 + 3 * k], tev[4 + 3 * k]);
+            tc += a; tg += b; tw += c;
+            int below = np - (k + 2) * NB; if (below < 0) below = 0;
+            double fl = (double) below * below * NB;
+            if (k % 4 == 0 || c > 0.5) fprintf(stderr, "[trace] k=%3d col %.3f ms  trailing %.3f ms (%.1f TF)  wait-panel %.3f ms\n", k, a, b, b > 0 ? fl / b / 1e9 : 0.0, c);
+        }
+        fprintf(stderr, "[trace] totals: col %.1f ms trailing %.1f ms wait %.1f ms\n", tc, tg, tw);
+        for (auto e : tev) cudaEventDestroy(e);
     }
     return HD_OK;
 }
