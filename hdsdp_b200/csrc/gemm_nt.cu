@@ -43,9 +43,12 @@ struct TileMap {
     int tiles_m, tiles_n, lower;
 };
 
-// linear CTA index -> (tm, tn); returns false if this CTA has no tile
+// linear CTA index -> (tm, tn); returns false if this CTA has no tile.  Super-tiles are GROUP m-tiles x
+// GROUP*(128/BN) n-tiles (a 1024 x 1024 block of C) so that consecutive CTAs share their A/B panels in L2.
+template <int BN>
 __device__ __forceinline__ bool map_tile(const TileMap &tmap, int bid, int &tm, int &tn) {
-    const int gsq = GROUP * GROUP;
+    constexpr int GN = GROUP * (128 / BN);
+    const int gsq = GROUP * GN;
     int super = bid / gsq, within = bid % gsq;
     int sm_, sn_;
     if (tmap.lower) {
@@ -56,23 +59,27 @@ __device__ __forceinline__ bool map_tile(const TileMap &tmap, int bid, int &tm, 
         sm_ = s;
         sn_ = super - s * (s + 1) / 2;
     } else {
-        int super_n = (tmap.tiles_n + GROUP - 1) / GROUP;
+        int super_n = (tmap.tiles_n + GN - 1) / GN;
         sm_ = super / super_n;
         sn_ = super % super_n;
     }
     tm = sm_ * GROUP + within % GROUP;
-    tn = sn_ * GROUP + within / GROUP;
+    tn = sn_ * GN + within / GROUP;
     if (tm >= tmap.tiles_m || tn >= tmap.tiles_n) return false;
-    if (tmap.lower && tn > tm) return false;
+    if (tmap.lower && tn * BN > tm * BM + BM - 1) return false;
     return true;
 }
 
-template <int BK, int STAGES>
-__global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
-    constexpr int STAGE_DOUBLES = 2 * BK * LDS_; // A tile + B tile
+// BN = 128: 8 warps (256 threads), one CTA per SM.  BN = 64: 4 warps (128 threads), two CTAs per SM, so one CTA's
+// barrier stalls and C read-modify-write epilogue overlap with the other CTA's main loop.
+template <int BN, int BK, int STAGES, int MINB>
+__global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
+    constexpr int NT = BN * 2;
+    constexpr int LDB_ = BN + 4;                          // 132 / 68: both = 4 (mod 16) -> conflict-free fragment loads
+    constexpr int STAGE_DOUBLES = BK * (LDS_ + LDB_);     // A tile + B tile
     extern __shared__ __align__(16) double smem[];
     int tm, tn;
-    if (!map_tile(tmap, blockIdx.x, tm, tn)) return;
+    if (!map_tile<BN>(tmap, blockIdx.x, tm, tn)) return;
     const int m0 = tm * BM, n0 = tn * BN;
 
     const int tid = threadIdx.x;
@@ -82,29 +89,29 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tm
     const int wn = (warp >> 1) * 32; // warp offset along n
 
     int k_lo = 0;
-    if (g.flags & HD_GEMM_KTRI_MAX) k_lo = max(m0, n0); // X[i,k] == 0 for k < i on both operands
+    if (g.flags & HD_GEMM_KTRI_MAX) k_lo = max(m0, n0) & ~(BK - 1); // X[i,k] == 0 for k < i on both operands
     const int nk = (g.K - k_lo) / BK;
 
     const double *Ag = g.A + (long) k_lo * g.lda + m0;
     const double *Bg = g.B + (long) k_lo * g.ldb + n0;
 
-    // cp.async mapping: each operand stage = BK k-rows x 128 doubles = BK*64 16-byte chunks
+    // cp.async mapping: A stage = BK k-rows x 128 doubles, B stage = BK k-rows x BN doubles, 16-byte chunks
     auto load_stage = [&](int stage, int kt) {
         double *As = smem + stage * STAGE_DOUBLES;
         double *Bs = As + BK * LDS_;
         const double *a = Ag + (long) kt * BK * g.lda;
         const double *b = Bg + (long) kt * BK * g.ldb;
 #pragma unroll
-        for (int i = 0; i < BK / 4; ++i) {
-            int c = tid + i * 256;
+        for (int i = 0; i < BK * 64 / NT; ++i) {
+            int c = tid + i * NT;
             int kr = c >> 6, mc = (c & 63) * 2;
             cp_async16(As + kr * LDS_ + mc, a + (long) kr * g.lda + mc);
         }
 #pragma unroll
-        for (int i = 0; i < BK / 4; ++i) {
-            int c = tid + i * 256;
-            int kr = c >> 6, nc = (c & 63) * 2;
-            cp_async16(Bs + kr * LDS_ + nc, b + (long) kr * g.ldb + nc);
+        for (int i = 0; i < BK * (BN / 2) / NT; ++i) {
+            int c = tid + i * NT;
+            int kr = c / (BN / 2), nc = (c % (BN / 2)) * 2;
+            cp_async16(Bs + kr * LDB_ + nc, b + (long) kr * g.ldb + nc);
         }
     };
 
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tm
         for (int kk = 0; kk < BK; kk += 4) {
             double bf[4], af[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) bf[i] = Bs[(kk + tig) * LDS_ + wn + 8 * i + gid];
+            for (int i = 0; i < 4; ++i) bf[i] = Bs[(kk + tig) * LDB_ + wn + 8 * i + gid];
 #pragma unroll
             for (int j = 0; j < 8; ++j) af[j] = As[(kk + tig) * LDS_ + wm + 8 * j + gid];
 #pragma unroll
@@ -182,9 +189,37 @@ __global__ void __launch_bounds__(256, 1) dgemm_nt_kernel(GemmArgs g, TileMap tm
 
 int g_num_sms = 0;
 bool g_attr_set = false;
-int g_variant = 1; // 0: BK=16 x 4 stages, 1: BK=32 x 3 stages
+int g_variant = 1; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x16 4 stages x2 CTAs; 3: 128x64x32 2 stages x2 CTAs
 
-template <int BK, int STAGES> constexpr int smem_bytes() { return STAGES * 2 * BK * LDS_ * 8; }
+template <int BN, int BK, int STAGES> constexpr int smem_bytes() { return STAGES * BK * (LDS_ + BN + 4) * 8; }
+
+template <int BN, int BK, int STAGES, int MINB>
+int launch_variant(cudaStream_t st, const GemmArgs &g) {
+    static bool attr = false;
+    if (!attr) {
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem_bytes<BN, BK, STAGES>()));
+        attr = true;
+    }
+    constexpr int GN = GROUP * (128 / BN);
+    TileMap tmap;
+    tmap.tiles_m = g.M / BM;
+    tmap.tiles_n = g.N / BN;
+    tmap.lower = (g.flags & HD_GEMM_LOWER) ? 1 : 0;
+    long nsuper;
+    if (tmap.lower) {
+        if (g.M != g.N) return HD_FAILED;
+        long s = (tmap.tiles_m + GROUP - 1) / GROUP;
+        nsuper = s * (s + 1) / 2;
+    } else {
+        nsuper = (long) ((tmap.tiles_m + GROUP - 1) / GROUP) * ((tmap.tiles_n + GN - 1) / GN);
+    }
+    long nblocks = nsuper * GROUP * GN;
+    ++g_hd_launches;
+    dgemm_nt_kernel<BN, BK, STAGES, MINB><<<(unsigned) nblocks, BN * 2, smem_bytes<BN, BK, STAGES>(), st>>>(g, tmap);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
 
 } // namespace
 
@@ -206,27 +241,10 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
         fprintf(stderr, "[hdsdpcu] gemm_nt: unpadded shape %d %d %d\n", g.M, g.N, g.K);
         return HD_FAILED;
     }
-    if (!g_attr_set) {
-        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<16, 4>()));
-        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<32, 3>()));
-        g_attr_set = true;
+    switch (g_variant) {
+        case 0: return launch_variant<128, 16, 4, 1>(st, g);
+        case 2: return launch_variant<64, 16, 4, 2>(st, g);
+        case 3: return launch_variant<64, 32, 2, 2>(st, g);
+        default: return launch_variant<128, 32, 3, 1>(st, g);
     }
-    TileMap tmap;
-    tmap.tiles_m = g.M / BM;
-    tmap.tiles_n = g.N / BN;
-    tmap.lower = (g.flags & HD_GEMM_LOWER) ? 1 : 0;
-    long nsuper;
-    if (tmap.lower) {
-        if (g.M != g.N) return HD_FAILED;
-        long s = (tmap.tiles_m + GROUP - 1) / GROUP;
-        nsuper = s * (s + 1) / 2;
-    } else {
-        nsuper = (long) ((tmap.tiles_m + GROUP - 1) / GROUP) * ((tmap.tiles_n + GROUP - 1) / GROUP);
-    }
-    long nblocks = nsuper * GROUP * GROUP;
-    ++g_hd_launches;
-    if (g_variant == 0) dgemm_nt_kernel<16, 4><<<(unsigned) nblocks, 256, smem_bytes<16, 4>(), st>>>(g, tmap);
-    else dgemm_nt_kernel<32, 3><<<(unsigned) nblocks, 256, smem_bytes<32, 3>(), st>>>(g, tmap);
-    HD_CUDA(cudaGetLastError());
-    return HD_OK;
 }

@@ -32,6 +32,7 @@ def ev_time(stream, fn, reps=3, warm=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true")
+    ap.add_argument("--variant", type=int, default=1)
     args = ap.parse_args()
     lib = _lib.require_gpu(0)
     st = torch.cuda.ExternalStream(lib.hdsdpcu_stream())
@@ -59,16 +60,17 @@ def main():
     del a, b, c
 
     # 2. our DMMA GEMM
-    shapes = [(4096, 4096, 4096, 0), (8192, 8192, 8192, 0), (8192, 8192, 8192, 1), (16384, 16384, 2048, 1), (16384, 16384, 512, 1), (16384, 128, 128, 0)]
+    shapes = [(4096, 4096, 4096, 0), (8192, 8192, 8192, 0), (16384, 16384, 2048, 1), (16384, 16384, 1024, 1), (16384, 16384, 512, 1), (16384, 128, 128, 0)]
     if args.big:
-        shapes += [(24576, 24576, 24576, 1)]
-    for variant in (0, 1):
+        shapes += [(32768, 32768, 1024, 1)]
+    for variant in (0, 1, 2, 3):
       lib.hdsdpcu_set_option(b"gemm_variant", variant)
       for (M, N, K, lower) in shapes:
         A = torch.randn(K, M, dtype=torch.float64, device="cuda"); B = torch.randn(K, N, dtype=torch.float64, device="cuda")
         C = torch.zeros(N, M, dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
-        fn = lambda: lib.hdsdpcu_dgemm_nt_dev(M, N, K, 1.0, A.data_ptr(), M, B.data_ptr(), N, 0.0, C.data_ptr(), M, lower)
+        beta = 1.0 if lower else 0.0   # lower shapes are the Cholesky trailing update: C -= A B^T (read-modify-write)
+        fn = lambda: lib.hdsdpcu_dgemm_nt_dev(M, N, K, -1.0 if lower else 1.0, A.data_ptr(), M, B.data_ptr(), N, beta, C.data_ptr(), M, lower)
         best, mean = ev_time(st, fn, reps=3, warm=1)
         flops = 2.0 * M * N * K * (0.5 if lower else 1.0)
         rec = {"probe": "dmma_gemm_nt", "variant": variant, "M": M, "N": N, "K": K, "lower": lower, "ms": best * 1e3, "tflops_best": flops / best / 1e12, "tflops_mean": flops / mean / 1e12}
@@ -80,7 +82,8 @@ def main():
 
     # 3. Cholesky / inverse / solves through the linsys device entry points
     import ctypes
-    for n, blk in ((2048, 0), (8192, 0), (8192, 1024), (16384, 0), (16384, 1024), (16384, 2048)) + (((32768, 1024), (32768, 2048)) if args.big else ()):
+    lib.hdsdpcu_set_option(b"gemm_variant", args.variant)
+    for n, blk in ((2048, 0), (8192, 1024), (16384, 1024)) + (((32768, 1024), (32768, 2048)) if args.big else ()):
         lib.hdsdpcu_set_option(b"chol_block", blk)
         h = ctypes.c_void_p()
         assert lib.hdsdpcu_linsys_create(ctypes.byref(h), n) == 0
