@@ -126,6 +126,17 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
         if (s < nk) load_stage(s, s);
         cp_async_commit();
     }
+    if (g.beta != 0.0 || (g.flags & HD_GEMM_EPI_HADSQ)) {
+        // C is read in the epilogue: pull this thread's 64-byte segments of the tile into L2 now (4 lanes share a segment)
+        if (tig == 0) {
+            const double *Cp = g.C + (long) (n0 + wn + gid) * g.ldc + m0 + wm;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp + (long) (8 * i) * g.ldc + 8 * j));
+        }
+    }
 
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
@@ -155,6 +166,33 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
     // epilogue: thread owns C[m .. m+1][n] with n = n0+wn+8i+gid, m = m0+wm+8j+2*tig
     const bool lower = (g.flags & HD_GEMM_LOWER) != 0;
     const bool hadsq = (g.flags & HD_GEMM_EPI_HADSQ) != 0;
+    const bool interior = !lower || (n0 + BN - 1 <= m0); // no entry of this tile lies above the diagonal
+    double *Cw = g.C + (long) (n0 + wn + gid) * g.ldc + m0 + wm + 2 * tig;
+    if (interior && !hadsq) {
+        if (g.beta == 0.0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+                    *reinterpret_cast<double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j) = v;
+                }
+        } else {
+            // read-modify-write in batches of 8 independent 16-byte loads (the C tile was prefetched into L2 above)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double2 old[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) old[j] = *reinterpret_cast<const double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    double2 v = make_double2(g.alpha * acc[i][j][0] + g.beta * old[j].x, g.alpha * acc[i][j][1] + g.beta * old[j].y);
+                    *reinterpret_cast<double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j) = v;
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int n = n0 + wn + 8 * i + gid;
