@@ -250,7 +250,7 @@ int chol_load_dev(cudaStream_t st, DenseChol *c, const double *dS, long lds) {
 //   side :            wait e_col -> potrf(A_{k+1,k+1}) -> A_{k+2..,k+1} <- A L^-T -> e_panel
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_ev_col = nullptr, g_ev_panel = nullptr;
-static int g_lookahead_nb = 1024; // block size; <= 0 disables the blocked path
+static int g_lookahead_nb = 2048; // block size; <= 0 disables the blocked path
 
 void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
 

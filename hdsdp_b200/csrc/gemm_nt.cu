@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
 
 int g_num_sms = 0;
 bool g_attr_set = false;
-int g_variant = 1; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x16 4 stages x2 CTAs; 3: 128x64x32 2 stages x2 CTAs
+int g_variant = 3; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x16 4 stages x2 CTAs; 3: 128x64x32 2 stages x2 CTAs
 
 template <int BN, int BK, int STAGES> constexpr int smem_bytes() { return STAGES * BK * (LDS_ + BN + 4) * 8; }
 
@@ -281,8 +281,8 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
     }
     switch (g_variant) {
         case 0: return launch_variant<128, 16, 4, 1>(st, g);
+        case 1: return launch_variant<128, 32, 3, 1>(st, g);
         case 2: return launch_variant<64, 16, 4, 2>(st, g);
-        case 3: return launch_variant<64, 32, 2, 2>(st, g);
-        default: return launch_variant<128, 32, 3, 1>(st, g);
+        default: return launch_variant<64, 32, 2, 2>(st, g);
     }
 }

@@ -31,8 +31,9 @@ const char *hdsdpcu_version(void);
 long hdsdpcu_launch_count(int reset);
 /* device-to-device copy on the library stream (bench plumbing for HBM-resident inputs) */
 int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes);
-/* tuning knobs for measurements: "gemm_variant" 0 = 128x128x16 tile, 4 stages; 1 = 128x128x32 tile, 3 stages (default);
- * "chol_block" NB of the blocked look-ahead Cholesky used when the padded dimension is >= 4 NB (default 1024; 0 = pure recursion) */
+/* tuning knobs for measurements: "gemm_variant" CTA tile / pipeline of the DMMA GEMM: 0 = 128x128x16, 4 stages;
+ * 1 = 128x128x32, 3 stages; 2 = 128x64x16, 4 stages, 2 CTAs/SM; 3 = 128x64x32, 2 stages, 2 CTAs/SM (default);
+ * "chol_block" NB of the blocked look-ahead Cholesky used when the padded dimension is >= 4 NB (default 2048; 0 = pure recursion) */
 int hdsdpcu_set_option(const char *name, int value);
 
 /* ---------------------------------------------------------------------------------------------
