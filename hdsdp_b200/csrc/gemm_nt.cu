@@ -279,6 +279,12 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
         fprintf(stderr, "[hdsdpcu] gemm_nt: unpadded shape %d %d %d\n", g.M, g.N, g.K);
         return HD_FAILED;
     }
+    // In-place products (C aliases A, used by the leaf triangular solves with N == 128) are only safe when ONE CTA
+    // owns all columns of its row block: the 64-wide tiles would let a sibling CTA overwrite rows still being read.
+    if (g.A == g.C || g.B == g.C) {
+        if (g.N != BN) return HD_FAILED;
+        return launch_variant<128, 32, 3, 1>(st, g);
+    }
     switch (g_variant) {
         case 0: return launch_variant<128, 16, 4, 1>(st, g);
         case 1: return launch_variant<128, 32, 3, 1>(st, g);
