@@ -298,7 +298,10 @@ def run_ours(args):
                        "schur_bytes": 8 * mp * mp, "l2_policy": "inputs larger than L2 (M is 20 GB; every step uses a new y)",
                        "step": "S update + Cholesky(S) + S^-1 + Schur M + regularize + Cholesky(M) + 2 solves", "setup_s": setup_s},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "kernel": "dgemm_nt_kernel (DMMA) inside Cholesky(M): m^3/3 flop per factorisation",
+                         "traffic": 21.28e9,
+                         "traffic_note": "dram__bytes_read+write of ONE representative dgemm_nt launch (32768^2 lower, K=2048: 2.2e12 of the "
+                                         "factorisation's 4.17e13 flop), ncu --set full, profiles/README.md; algorithmic 9.1e9 B for that launch",
+                         "kernel": "dgemm_nt_kernel (DMMA) inside Cholesky(M): m^3/3 flop per factorisation",
                          "peak_source": "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry)",
                          "factorize_ms": fact_s * 1e3, "share_of_step": fact_s / per_step},
             "e2e": {"value": e2e_s / args.steps, "unit": "s/iteration", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
