@@ -192,6 +192,14 @@ def run_ours(args):
     cone.set_start(RD)
     setup_s = time.time() - t0
     mp = lib.hdsdpcu_kkt_padded_dim(kkt.h)
+    if world > 1:
+        # strong scaling: the SAME m = 50k problem; M is assembled and factored 1-D block-cyclic over the ranks, factor
+        # panels travel over NVLink peer memory (hdsdp_b200/csrc/dist.cu); NCCL is used for this handshake and the barriers only
+        def allgather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        kkt.dist_init(rank, world, args.dist_block, allgather)
 
     peak = cublas_dgemm_peak(torch) if (rank == 0 and not args.no_peak) else 0.0
 
@@ -289,19 +297,20 @@ def run_ours(args):
         per_step = dev_s / args.steps
         chol_flops = float(m) ** 3 / 3.0
         fact_s = float(np.mean(fact_ms)) * 1e-3
-        achieved = chol_flops / fact_s / 1e12
+        achieved = chol_flops / fact_s / 1e12 / world   # per GPU, against the single-GPU peak
         line = {
             "metric": "sec/IPM iteration (Schur build + Cholesky) at m=50k", "value": per_step, "unit": "s/iteration", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"theta n={n} m={m} (BASELINE.json configs[3])", "cone_dim": n, "constraints": m,
                        "schur_bytes": 8 * mp * mp, "l2_policy": "inputs larger than L2 (M is 20 GB; every step uses a new y)",
+                       "parallelism": (f"M 1-D block-cyclic (nb={args.dist_block}) over {world} GPUs, peer-memory panel exchange; S-side work replicated" if world > 1 else "single GPU"),
                        "step": "S update + Cholesky(S) + S^-1 + Schur M + regularize + Cholesky(M) + 2 solves", "setup_s": setup_s},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": 21.28e9,
                          "traffic_note": "dram__bytes_read+write of ONE representative dgemm_nt launch (32768^2 lower, K=2048: 2.2e12 of the "
                                          "factorisation's 4.17e13 flop), ncu --set full, profiles/README.md; algorithmic 9.1e9 B for that launch",
-                         "kernel": "dgemm_nt_kernel (DMMA) inside Cholesky(M): m^3/3 flop per factorisation",
+                         "kernel": "dgemm_nt_kernel (DMMA) inside Cholesky(M): m^3/3 flop per factorisation" + (f", split over {world} GPUs (achieved is per GPU)" if world > 1 else ""),
                          "peak_source": "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry)",
                          "factorize_ms": fact_s * 1e3, "share_of_step": fact_s / per_step},
             "e2e": {"value": e2e_s / args.steps, "unit": "s/iteration", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -334,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=THETA_N)
     ap.add_argument("--edges", type=int, default=THETA_EDGES)
+    ap.add_argument("--dist-block", type=int, default=512, help="block-column width of the multi-GPU distribution of M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true", help="skip the live cuBLAS DGEMM peak measurement (ncu runs)")
     args = ap.parse_args()

@@ -93,6 +93,13 @@ _SIGNATURES = {
     "hdsdpcu_kkt_asinv_dev": (c_void_p, [c_void_p]),
     "hdsdpcu_kkt_solve_dev": (c_int, [c_void_p, c_int, c_void_p]),
     "hdsdpcu_kkt_setshard": (c_int, [c_void_p, c_int, c_int]),
+    # multi-GPU Schur matrix
+    "hdsdpcu_dist_blob_bytes": (c_int, []),
+    "hdsdpcu_dist_owner": (c_int, [c_int, c_int, c_int]),
+    "hdsdpcu_kkt_dist_init": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "hdsdpcu_kkt_dist_export": (c_int, [c_void_p, c_void_p]),
+    "hdsdpcu_kkt_dist_connect": (c_int, [c_void_p, c_void_p]),
+    "hdsdpcu_distchol_selftest": (c_int, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
     "hdsdpcu_dgemm_nt_dev": (c_int, [c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double, c_void_p, c_long, c_int]),
 }
 

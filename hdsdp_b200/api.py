@@ -252,6 +252,22 @@ class KKT:
     def set_shard(self, rank: int, nranks: int):
         check(self.lib.hdsdpcu_kkt_setshard(self.h, rank, nranks), "setshard")
 
+    def dist_init(self, rank: int, nranks: int, block: int = 512, allgather=None):
+        """Multi-GPU Schur matrix (one process per GPU): 1-D block-cyclic column ownership, peer-memory panel exchange.
+        `allgather(bytes) -> list[bytes]` gathers the IPC blobs in rank order (torch.distributed, MPI, ...)."""
+        check(self.lib.hdsdpcu_kkt_dist_init(self.h, rank, nranks, block), "kkt_dist_init")
+        self.rank, self.nranks, self.block = rank, nranks, block
+        if nranks == 1:
+            return
+        import ctypes
+        nbytes = self.lib.hdsdpcu_dist_blob_bytes()
+        blob = ctypes.create_string_buffer(nbytes)
+        check(self.lib.hdsdpcu_kkt_dist_export(self.h, blob), "kkt_dist_export")
+        blobs = allgather(blob.raw)
+        assert len(blobs) == nranks and all(len(b) == nbytes for b in blobs)
+        allb = ctypes.create_string_buffer(b"".join(blobs), nbytes * nranks)
+        check(self.lib.hdsdpcu_kkt_dist_connect(self.h, allb), "kkt_dist_connect")
+
     def build_up(self, type_kkt: int = KKT_TYPE_INFEASIBLE):
         check(self.lib.hdsdpcu_kkt_buildup(self.h, int(type_kkt)), "HKKTBuildUp")
 

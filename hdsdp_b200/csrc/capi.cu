@@ -474,8 +474,70 @@ int hdsdpcu_kkt_solve_dev(void *kkt, int nRhs, double *d_x) { return kkt_solve_d
 int hdsdpcu_kkt_setshard(void *kkt, int rank, int nRanks) {
     KktCU *k = (KktCU *) kkt;
     if (nRanks < 1 || rank < 0 || rank >= nRanks) return HD_FAILED;
-    k->rank = rank; k->nranks = nRanks;
+    k->rank = rank; k->nranks = nRanks; k->shard_nb = HD_LEAF;
     return HD_OK;
+}
+
+// ---- multi-GPU factorisation of M (dist.cu) ----------------------------------------------------
+int hdsdpcu_dist_blob_bytes(void) { return 3 * (int) sizeof(cudaIpcMemHandle_t); }
+int hdsdpcu_dist_owner(int col, int blockSize, int nRanks) { return (blockSize > 0 && nRanks > 0) ? (col / blockSize) % nRanks : -1; }
+
+int hdsdpcu_kkt_dist_init(void *kkt, int rank, int nRanks, int blockSize) {
+    HD_CALL(ensure_ready());
+    KktCU *k = (KktCU *) kkt;
+    if (nRanks < 1 || rank < 0 || rank >= nRanks || blockSize < HD_LEAF || blockSize % HD_LEAF || k->dist) return HD_FAILED;
+    k->rank = rank; k->nranks = nRanks; k->shard_nb = blockSize;
+    if (nRanks == 1) return HD_OK;
+    DenseChol *chols[1] = {k->chol};
+    HD_CALL(dist_create(&k->dist, k->m, blockSize, nRanks, 1, &rank, chols, g_stream));
+    HD_CUDA(cudaMalloc(&k->d_gather, sizeof(double) * 16 * 8));
+    return HD_OK;
+}
+int hdsdpcu_kkt_dist_export(void *kkt, void *blob) {
+    KktCU *k = (KktCU *) kkt;
+    if (!k->dist) return HD_FAILED;
+    return dist_export(k->dist, 0, blob);
+}
+int hdsdpcu_kkt_dist_connect(void *kkt, const void *blobs) {
+    KktCU *k = (KktCU *) kkt;
+    if (!k->dist) return HD_FAILED;
+    return dist_connect(k->dist, blobs);
+}
+
+// The whole distributed schedule with nRanks ranks living in this process on the current device (CUDA events
+// instead of peer flags): rank r gets only the block columns it owns (the rest of its buffer is poisoned with NaN),
+// every rank must end up with the complete factor.  outL[r] (n x n, lower meaningful) for r = 0 and nRanks-1.
+int hdsdpcu_distchol_selftest(int n, int blockSize, int nRanks, const double *A, double *outL0, double *outLlast, int *info) {
+    HD_CALL(ensure_ready());
+    if (nRanks < 1 || nRanks > 16) return HD_FAILED;
+    DistChol *d = nullptr;
+    int ranks[16];
+    for (int r = 0; r < nRanks; ++r) ranks[r] = r;
+    HD_CALL(dist_create(&d, n, blockSize, nRanks, nRanks, ranks, nullptr, nullptr));
+    const int np = hd_pad(n);
+    std::vector<double> stage((size_t) np * np);
+    int rc = HD_OK;
+    for (int r = 0; r < nRanks && rc == HD_OK; ++r) {
+        DenseChol *c = dist_local_chol(d, r);
+        for (int j = 0; j < np; ++j) {
+            const bool mine = (j / blockSize) % nRanks == r;
+            for (int i = 0; i < np; ++i) {
+                double v = __builtin_nan("");
+                if (mine && i >= (j / blockSize) * blockSize) v = (i < n && j < n) ? A[(size_t) j * n + i] : (i == j ? 1.0 : 0.0);
+                stage[(size_t) j * np + i] = v;
+            }
+        }
+        if (cudaMemcpy(c->L, stage.data(), sizeof(double) * (size_t) np * np, cudaMemcpyHostToDevice) != cudaSuccess) rc = HD_FAILED;
+    }
+    if (rc == HD_OK) rc = dist_factor(d, info);
+    for (int pass = 0; pass < 2 && rc == HD_OK; ++pass) {
+        double *out = pass == 0 ? outL0 : outLlast;
+        if (!out) continue;
+        DenseChol *c = dist_local_chol(d, pass == 0 ? 0 : nRanks - 1);
+        if (cudaMemcpy2D(out, (size_t) n * 8, c->L, (size_t) np * 8, (size_t) n * 8, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = HD_FAILED;
+    }
+    dist_destroy(d);
+    return rc;
 }
 
 int hdsdpcu_dgemm_nt_dev(int M, int N, int K, double alpha, const double *dA, long lda, const double *dB, long ldb,

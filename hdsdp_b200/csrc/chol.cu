@@ -193,6 +193,25 @@ int invert_rec(cudaStream_t st, const double *L, long ldl, int n, const double *
 
 } // namespace
 
+int hd_potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base) {
+    static unsigned long long attr = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr >> (dev & 63) & 1ull)) {
+        HD_CUDA(cudaFuncSetAttribute(potf2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+        attr |= 1ull << (dev & 63);
+    }
+    return potrf_rec(st, A, lda, n, dinv, info, base);
+}
+int hd_trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, long ldl, int n, const double *dinv) {
+    return trsm_rec(st, B, ldb, rows, L, ldl, n, dinv);
+}
+int hd_chol_finish(cudaStream_t st, DenseChol *c) {
+    HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
 int chol_create(DenseChol **pc, int n) {
     if (n <= 0) return HD_FAILED;
     DenseChol *c = (DenseChol *) calloc(1, sizeof(DenseChol));

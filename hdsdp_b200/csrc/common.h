@@ -57,6 +57,7 @@ enum : int {
     HD_GEMM_EPI_HADSQ = 4,  // epilogue C += sa[m]*sb[n]*acc^2 (rank-one Schur, M2)
 };
 
+struct DenseChol;
 struct GemmArgs {
     int M, N, K;
     const double *A; long lda;
@@ -66,9 +67,16 @@ struct GemmArgs {
     int flags;
     const double *sa;   // HADSQ: scale over m
     const double *sb;   // HADSQ: scale over n
+    // block-cyclic N (distributed Cholesky, dist.cu): the N dimension enumerates only the column blocks this rank owns.
+    // Local column c lives at global column (c / bc_nb) * bc_stride + c % bc_nb (relative to B / C); 0 = contiguous.
+    int bc_nb, bc_stride;
 };
 
 int hd_gemm_nt(cudaStream_t st, const GemmArgs &g);
+// recursive kernels of chol.cu, enqueue-only (used by the single-GPU driver and by dist.cu)
+int hd_potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base);
+int hd_trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, long ldl, int n, const double *dinv);
+int hd_chol_finish(cudaStream_t st, DenseChol *c); // transposed inverse leaves for the L^T solve
 int hd_num_sms();
 void hd_gemm_set_variant(int v);
 void hd_chol_set_block(int nb);

@@ -108,8 +108,9 @@ __global__ void axpy_lower_kernel(double *dst, const double *src, long ld, int n
 // ---------------------------------------------------------------------------------------------
 // Schur kernels
 // ---------------------------------------------------------------------------------------------
-struct Shard { int rank, nranks; };
-__device__ __forceinline__ bool owns_col(const Shard &s, int col) { return s.nranks <= 1 || ((col >> 7) % s.nranks) == s.rank; }
+// multi-GPU assembly: Schur column c belongs to rank (c / nb) % nranks (1-D block-cyclic, the layout dist.cu factors in)
+struct Shard { int rank, nranks, nb; };
+__device__ __forceinline__ bool owns_col(const Shard &s, int col) { return s.nranks <= 1 || ((col / s.nb) % s.nranks) == s.rank; }
 
 // R x R, unit vectors: M[ci, cj] += s_i s_j Sinv[k_i, k_j]^2  (i >= j).  32x32 tiles.
 __global__ void __launch_bounds__(256) r1_unit_schur_kernel(const double *__restrict__ Sinv, long lds,
@@ -745,11 +746,11 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
     const int n = c->n, np = c->np;
     const long ldm = k->mp;
     const double rd = c->dualResidual;
-    Shard sh{k->rank, k->nranks};
+    Shard sh{k->rank, k->nranks, k->shard_nb};
     const bool build_matrix = (typeKKT != KKT_CORRECTOR);
     const bool hsd = (typeKKT == KKT_HOMOGENEOUS);
-    // on rank > 0 the side vectors are produced by rank 0 only (they are replicated work otherwise)
-    const bool do_vectors = (k->rank == 0);
+    // the side vectors are O(nnz n) work: every rank computes all of them (each process is a full replica of the host solver)
+    const bool do_vectors = true;
 
     // ---- 1. "S^-1" ----------------------------------------------------------------------------
     if (typeKKT == KKT_PRIMAL) {

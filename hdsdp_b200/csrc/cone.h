@@ -28,6 +28,7 @@ struct HostCoeff {
 struct SsGroup { int first, count, ent_first, ent_count; };
 
 struct KktCU;
+struct DistChol;
 
 struct ConeCU {
     int m = 0;   // constraints
@@ -108,10 +109,23 @@ struct KktCU {
     std::vector<double *> primalX; // host pointers registered by HKKTRegisterPSDP
     bool factored = false;
     // multi-GPU column sharding of the Schur assembly (rank r builds columns j with (j/128) % nranks == r)
-    int rank = 0, nranks = 1;
+    int rank = 0, nranks = 1, shard_nb = HD_LEAF;
+    struct DistChol *dist = nullptr; // distributed factorisation of M (dist.cu); null on one GPU
+    double *d_gather = nullptr;      // [16 x 8] all-gather scratch
 };
 
 cudaStream_t hd_stream();
+
+// dist.cu
+int dist_create(DistChol **pd, int n, int nb, int P, int nlocal, const int *ranks, DenseChol **chols, cudaStream_t main_stream);
+void dist_destroy(DistChol *d);
+DenseChol *dist_local_chol(DistChol *d, int li);
+cudaStream_t dist_local_stream(DistChol *d, int li);
+int dist_block(const DistChol *d);
+int dist_export(DistChol *d, int li, void *blob);   // 192 bytes
+int dist_connect(DistChol *d, const void *blobs);    // P x 192 bytes, rank order
+int dist_factor(DistChol *d, int *info_out);
+int dist_allgather_small(DistChol *d, const double *d_val, int cnt, double *d_out);
 
 int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx, const double *elem);
 void cone_destroy(ConeCU *c);

@@ -1,0 +1,391 @@
+// hdsdp_b200/csrc/dist.cu -- multi-GPU Cholesky of the Schur matrix M over NVLink peer memory.
+//
+// Replaces, for m large enough to matter (config D: m = 50 000), the single dpotrf behind the reference's
+// HKKTFactorize (interface/hdsdp_schur.c:328, linalg/hdsdp_linsolver.c:1096).  SURVEY section 8(e).
+//
+// Layout.  P ranks (one process per GPU, or several "ranks" inside one process for tests).  M is cut into block
+// columns of width nb; block column j belongs to rank j % P (1-D block-cyclic).  Every rank keeps a FULL mp x mp
+// buffer L (20 GB at m = 50k out of 180 GB HBM): its own block columns hold M on entry (the Schur assembly writes
+// them there directly, cone.cu `owns_col`) and are updated in place; the block columns of the other ranks receive
+// the finished factor panels.  On exit every rank holds the complete factor, so the triangular solves that follow
+// (2..26 per factorisation) run locally without any communication.
+//
+// Algorithm: right-looking with one step of look-ahead.  At step k every rank applies panel k to the block columns
+// it owns with ONE DMMA GEMM launch (gemm_nt.cu, block-cyclic N enumeration).  The owner of block k+1 first updates
+// only that block column, then factors it on a high-priority side stream (recursive potrf + panel trsm, chol.cu)
+// and pushes the panel to the peers while its main stream continues with the rest of its trailing update.
+//
+// Transport.  No collective library on the data path: the owner copies its finished panel straight into the
+// peers' L buffers (IPC-mapped peer memory, copy engines over NVLink / NVSwitch) in ring order starting with the
+// next owner -- the only rank whose critical path waits for it -- and then publishes a sequence number in the
+// peer's control block (st.release.sys).  Consumers wait for that number with a one-thread acquire spin on their
+// own GPU (bounded by a timeout).  Ranks that live in the same process are synchronised with CUDA events instead,
+// which is what lets the whole schedule run -- and be tested -- with P ranks on a single GPU.
+#include "common.h"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr int MAXP = 16;
+constexpr int CTRL_BYTES = 8192;
+constexpr int MAIL_OFF = 4096;      // doubles: mail[2][MAXP][8]
+constexpr int MAIL_CNT = 8;
+constexpr long long WAIT_TIMEOUT_NS = 30ll * 1000 * 1000 * 1000;
+
+// control block (ints): [0,P) panel sequence from src | [P,2P) ready epoch from src | [2P,3P) info from src |
+//                       [3P,4P) mail sequence from src | [4P] timeout flag
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void flag_write_kernel(int *remote_flag, int value, int *remote_info, const int *local_info) {
+    if (remote_info) *remote_info = *local_info;
+    __threadfence_system();
+    st_release_sys(remote_flag, value);
+}
+
+__global__ void flag_wait_kernel(const int *flag, int target, int *err) {
+    const long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < target) {
+        __nanosleep(100);
+        if (global_ns() - t0 > WAIT_TIMEOUT_NS) { *err = 1; return; }
+    }
+}
+
+struct MailDst { double *mail[MAXP]; int *flag[MAXP]; int n; };
+
+// val[cnt] -> this rank's slot in every peer's mailbox, then publish seq
+__global__ void mail_publish_kernel(MailDst dst, const double *val, int cnt, int seq) {
+    const int t = threadIdx.x;
+    for (int q = 0; q < dst.n; ++q)
+        if (t < cnt) dst.mail[q][t] = val[t];
+    __syncwarp();
+    __threadfence_system();
+    if (t == 0)
+        for (int q = 0; q < dst.n; ++q) st_release_sys(dst.flag[q], seq);
+}
+
+// wait for every peer's mail of sequence seq, then out[q*cnt + t] = mail_q[t] (own slot from val)
+__global__ void mail_collect_kernel(const char *ctrl, int P, int self, int seq, const double *val, int cnt, double *out, int *err) {
+    const int *ints = (const int *) ctrl;
+    const double *mail = (const double *) (ctrl + MAIL_OFF) + (size_t) (seq & 1) * MAXP * MAIL_CNT;
+    const int q = threadIdx.x;
+    if (q < P && q != self) {
+        const long long t0 = global_ns();
+        while (ld_acquire_sys(ints + 3 * P + q) < seq) {
+            __nanosleep(100);
+            if (global_ns() - t0 > WAIT_TIMEOUT_NS) { *err = 1; break; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * cnt; i += blockDim.x) {
+        const int r = i / cnt, t = i % cnt;
+        out[i] = (r == self) ? val[t] : mail[r * MAIL_CNT + t];
+    }
+}
+} // namespace
+
+struct DistRank {
+    int rank = 0, dev = 0;
+    DenseChol *chol = nullptr;
+    bool own_chol = false, own_stream = false;
+    cudaStream_t st = nullptr, side = nullptr, push = nullptr;
+    cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_ready = nullptr;
+    std::vector<cudaEvent_t> ev_recv; // per panel, recorded on the sender's push stream (same-process delivery)
+    char *ctrl = nullptr;
+    int *h_ctrl = nullptr;
+    struct Peer {
+        DistRank *local = nullptr;
+        double *L = nullptr, *Dinv = nullptr;
+        char *ctrl = nullptr;
+        bool ipc = false;
+    } peer[MAXP];
+    int ready_epoch_seen[MAXP] = {0};
+};
+
+struct DistChol {
+    int n = 0, mp = 0, nb = 0, nblk = 0, P = 1;
+    int nlocal = 0;
+    DistRank *local[MAXP] = {nullptr};
+    int epoch = 0, mail_seq = 0;
+    bool connected = false;
+};
+
+namespace {
+
+inline int blk_size(const DistChol *d, int k) { return (k == d->nblk - 1) ? d->mp - k * d->nb : d->nb; }
+inline DistRank *local_rank(DistChol *d, int rank) {
+    for (int i = 0; i < d->nlocal; ++i)
+        if (d->local[i]->rank == rank) return d->local[i];
+    return nullptr;
+}
+inline int *ctrl_ints(char *c) { return (int *) c; }
+inline int panel_seq(const DistChol *d, int k) { return d->epoch * (d->nblk + 1) + k + 1; }
+
+int push_panel(DistChol *d, DistRank *R, int k) {
+    const int P = d->P, nb = d->nb, mp = d->mp;
+    const int s0 = k * nb, bk = blk_size(d, k);
+    HD_CUDA(cudaStreamWaitEvent(R->push, R->ev_panel, 0));
+    const size_t off = (size_t) s0 * mp + s0;
+    const size_t leaf_off = (size_t) (s0 / HD_LEAF) * HD_LEAF * HD_LEAF;
+    for (int i = 1; i < P; ++i) {
+        const int q = (R->rank + i) % P; // ring order: the next owner (rank + 1) is served first
+        DistRank::Peer &pe = R->peer[q];
+        if (R->ready_epoch_seen[q] != d->epoch) {
+            // the peer's buffers may still be read by its previous solves: wait until it entered this factorisation
+            if (pe.local) HD_CUDA(cudaStreamWaitEvent(R->push, pe.local->ev_ready, 0));
+            else HDK(flag_wait_kernel)<<<1, 1, 0, R->push>>>(ctrl_ints(R->ctrl) + P + q, d->epoch, ctrl_ints(R->ctrl) + 4 * P);
+            R->ready_epoch_seen[q] = d->epoch;
+        }
+        double *dstL = pe.local ? pe.local->chol->L : pe.L;
+        double *dstD = pe.local ? pe.local->chol->Dinv : pe.Dinv;
+        HD_CUDA(cudaMemcpy2DAsync(dstL + off, (size_t) mp * 8, R->chol->L + off, (size_t) mp * 8, (size_t) (mp - s0) * 8, bk,
+                                  cudaMemcpyDefault, R->push));
+        HD_CUDA(cudaMemcpyAsync(dstD + leaf_off, R->chol->Dinv + leaf_off, sizeof(double) * (size_t) (bk / HD_LEAF) * HD_LEAF * HD_LEAF,
+                                cudaMemcpyDefault, R->push));
+        if (pe.local) {
+            HD_CUDA(cudaEventRecord(pe.local->ev_recv[k], R->push));
+        } else {
+            HDK(flag_write_kernel)<<<1, 1, 0, R->push>>>(ctrl_ints(pe.ctrl) + R->rank, panel_seq(d, k), ctrl_ints(pe.ctrl) + 2 * P + R->rank,
+                                                       R->chol->dinfo);
+        }
+    }
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+int factor_panel(DistChol *d, DistRank *R, int k) {
+    // side stream: Cholesky of the diagonal block of block column k and the triangular solve of the rows below it
+    const int nb = d->nb, mp = d->mp;
+    const int s = k * nb, b = blk_size(d, k), below = mp - s - b;
+    double *L = R->chol->L;
+    double *leaves = R->chol->Dinv + (size_t) (s / HD_LEAF) * HD_LEAF * HD_LEAF;
+    HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_col, 0));
+    HD_CALL(hd_potrf_rec(R->side, L + (size_t) s * mp + s, mp, b, leaves, R->chol->dinfo, s));
+    if (below > 0) HD_CALL(hd_trsm_rec(R->side, L + (size_t) s * mp + s + b, mp, below, L + (size_t) s * mp + s, mp, b, leaves));
+    HD_CUDA(cudaEventRecord(R->ev_panel, R->side));
+    return push_panel(d, R, k);
+}
+
+} // namespace
+
+int dist_create(DistChol **pd, int n, int nb, int P, int nlocal, const int *ranks, DenseChol **chols, cudaStream_t main_stream) {
+    if (P < 1 || P > MAXP || nlocal < 1 || nlocal > P || nb < HD_LEAF || nb % HD_LEAF) return HD_FAILED;
+    DistChol *d = new DistChol();
+    d->n = n; d->mp = hd_pad(n); d->nb = nb; d->P = P; d->nlocal = nlocal;
+    d->nblk = (d->mp + nb - 1) / nb;
+    int lo = 0, hi = 0;
+    HD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int i = 0; i < nlocal; ++i) {
+        DistRank *R = new DistRank();
+        d->local[i] = R;
+        R->rank = ranks[i];
+        HD_CUDA(cudaGetDevice(&R->dev));
+        if (chols && chols[i]) R->chol = chols[i];
+        else { HD_CALL(chol_create(&R->chol, n)); R->own_chol = true; }
+        if (main_stream && nlocal == 1) R->st = main_stream;
+        else { HD_CUDA(cudaStreamCreateWithFlags(&R->st, cudaStreamNonBlocking)); R->own_stream = true; }
+        HD_CUDA(cudaStreamCreateWithPriority(&R->side, cudaStreamNonBlocking, hi));
+        HD_CUDA(cudaStreamCreateWithPriority(&R->push, cudaStreamNonBlocking, hi));
+        HD_CUDA(cudaEventCreateWithFlags(&R->ev_col, cudaEventDisableTiming));
+        HD_CUDA(cudaEventCreateWithFlags(&R->ev_panel, cudaEventDisableTiming));
+        HD_CUDA(cudaEventCreateWithFlags(&R->ev_ready, cudaEventDisableTiming));
+        R->ev_recv.resize(d->nblk);
+        for (auto &e : R->ev_recv) HD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        HD_CUDA(cudaMalloc(&R->ctrl, CTRL_BYTES));
+        HD_CUDA(cudaMemset(R->ctrl, 0, CTRL_BYTES));
+        HD_CUDA(cudaMallocHost(&R->h_ctrl, CTRL_BYTES));
+    }
+    for (int i = 0; i < nlocal; ++i)
+        for (int j = 0; j < nlocal; ++j)
+            if (i != j) d->local[i]->peer[d->local[j]->rank].local = d->local[j];
+    d->connected = (nlocal == P);
+    *pd = d;
+    return HD_OK;
+}
+
+void dist_destroy(DistChol *d) {
+    if (!d) return;
+    for (int i = 0; i < d->nlocal; ++i) {
+        DistRank *R = d->local[i];
+        for (int q = 0; q < d->P; ++q)
+            if (R->peer[q].ipc) { cudaIpcCloseMemHandle(R->peer[q].L); cudaIpcCloseMemHandle(R->peer[q].Dinv); cudaIpcCloseMemHandle(R->peer[q].ctrl); }
+        if (R->own_chol) chol_destroy(R->chol);
+        if (R->own_stream) cudaStreamDestroy(R->st);
+        cudaStreamDestroy(R->side); cudaStreamDestroy(R->push);
+        cudaEventDestroy(R->ev_col); cudaEventDestroy(R->ev_panel); cudaEventDestroy(R->ev_ready);
+        for (auto &e : R->ev_recv) cudaEventDestroy(e);
+        cudaFree(R->ctrl); cudaFreeHost(R->h_ctrl);
+        delete R;
+    }
+    delete d;
+}
+
+DenseChol *dist_local_chol(DistChol *d, int li) { return d->local[li]->chol; }
+cudaStream_t dist_local_stream(DistChol *d, int li) { return d->local[li]->st; }
+int dist_block(const DistChol *d) { return d->nb; }
+
+// 3 IPC handles (L, Dinv, control block) of local rank li
+int dist_export(DistChol *d, int li, void *blob) {
+    DistRank *R = d->local[li];
+    cudaIpcMemHandle_t h[3];
+    HD_CUDA(cudaIpcGetMemHandle(&h[0], R->chol->L));
+    HD_CUDA(cudaIpcGetMemHandle(&h[1], R->chol->Dinv));
+    HD_CUDA(cudaIpcGetMemHandle(&h[2], R->ctrl));
+    memcpy(blob, h, sizeof(h));
+    return HD_OK;
+}
+
+// blobs: P consecutive export blobs in rank order (the entries of local ranks are ignored)
+int dist_connect(DistChol *d, const void *blobs) {
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *) blobs;
+    for (int i = 0; i < d->nlocal; ++i) {
+        DistRank *R = d->local[i];
+        for (int q = 0; q < d->P; ++q) {
+            if (q == R->rank || R->peer[q].local || R->peer[q].ipc) continue;
+            void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+            HD_CUDA(cudaIpcOpenMemHandle(&p0, h[3 * q + 0], cudaIpcMemLazyEnablePeerAccess));
+            HD_CUDA(cudaIpcOpenMemHandle(&p1, h[3 * q + 1], cudaIpcMemLazyEnablePeerAccess));
+            HD_CUDA(cudaIpcOpenMemHandle(&p2, h[3 * q + 2], cudaIpcMemLazyEnablePeerAccess));
+            R->peer[q].L = (double *) p0; R->peer[q].Dinv = (double *) p1; R->peer[q].ctrl = (char *) p2;
+            R->peer[q].ipc = true;
+        }
+    }
+    d->connected = true;
+    return HD_OK;
+}
+
+// Factor.  On entry the block columns owned by each local rank hold M (lower part, rows >= the block's first row,
+// identity padded); on exit every local rank's buffer holds the complete factor and all inverse leaves.
+int dist_factor(DistChol *d, int *info_out) {
+    if (!d->connected) return HD_FAILED;
+    d->epoch++;
+    const int P = d->P, nb = d->nb, mp = d->mp, nblk = d->nblk;
+    // ---- 0. enter the factorisation: reset info, tell the peers our buffers may be written -----------------------
+    for (int i = 0; i < d->nlocal; ++i) {
+        DistRank *R = d->local[i];
+        HD_CUDA(cudaSetDevice(R->dev));
+        HD_CUDA(cudaMemsetAsync(R->chol->dinfo, 0, sizeof(int), R->st));
+        HD_CUDA(cudaEventRecord(R->ev_ready, R->st));
+        HD_CUDA(cudaEventRecord(R->ev_col, R->st));
+        for (int q = 0; q < P; ++q) {
+            if (q == R->rank || R->peer[q].local) continue;
+            HDK(flag_write_kernel)<<<1, 1, 0, R->st>>>(ctrl_ints(R->peer[q].ctrl) + P + R->rank, d->epoch, nullptr, nullptr);
+        }
+        R->chol->factored = false;
+    }
+    // ---- panel 0 -----------------------------------------------------------------------------------------------------
+    if (DistRank *R = local_rank(d, 0)) {
+        HD_CUDA(cudaSetDevice(R->dev));
+        HD_CALL(factor_panel(d, R, 0));
+    }
+    for (int k = 0; k < nblk; ++k) {
+        const int owner = k % P;
+        // (1) every rank obtains panel k
+        for (int i = 0; i < d->nlocal; ++i) {
+            DistRank *R = d->local[i];
+            HD_CUDA(cudaSetDevice(R->dev));
+            if (R->rank == owner) {
+                HD_CUDA(cudaStreamWaitEvent(R->st, R->ev_panel, 0));
+            } else if (R->peer[owner].local) {
+                HD_CUDA(cudaStreamWaitEvent(R->st, R->ev_recv[k], 0));
+            } else {
+                HDK(flag_wait_kernel)<<<1, 1, 0, R->st>>>(ctrl_ints(R->ctrl) + owner, panel_seq(d, k), ctrl_ints(R->ctrl) + 4 * P);
+            }
+        }
+        if (k == nblk - 1) break;
+        const int s0 = k * nb, bk = blk_size(d, k);
+        const int next = (k + 1) % P;
+        // (2) the owner of block k+1 updates that block column first, then factors and ships it from its side streams
+        if (DistRank *R = local_rank(d, next)) {
+            HD_CUDA(cudaSetDevice(R->dev));
+            const int s1 = (k + 1) * nb, b1 = blk_size(d, k + 1);
+            const double *Pk = R->chol->L + (size_t) s0 * mp;
+            GemmArgs g{};
+            g.M = mp - s1; g.N = b1; g.K = bk;
+            g.A = Pk + s1; g.lda = mp; g.B = Pk + s1; g.ldb = mp; g.C = R->chol->L + (size_t) s1 * mp + s1; g.ldc = mp;
+            g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+            g.bc_nb = b1; g.bc_stride = b1;
+            HD_CALL(hd_gemm_nt(R->st, g));
+            HD_CUDA(cudaEventRecord(R->ev_col, R->st));
+            HD_CALL(factor_panel(d, R, k + 1));
+        }
+        // (3) everybody: the rest of the owned block columns j > k in one launch
+        for (int i = 0; i < d->nlocal; ++i) {
+            DistRank *R = d->local[i];
+            int j0 = k + 1 + ((R->rank - (k + 1)) % P + P) % P; // first owned block > k
+            if (j0 == k + 1 && R->rank == next) j0 += P;       // already done in (2)
+            if (j0 >= nblk) continue;
+            HD_CUDA(cudaSetDevice(R->dev));
+            const int cnt = (nblk - 1 - j0) / P + 1;
+            const int ms = j0 * nb;
+            const double *Pk = R->chol->L + (size_t) s0 * mp;
+            GemmArgs g{};
+            g.M = mp - ms; g.N = cnt * nb; g.K = bk;
+            g.A = Pk + ms; g.lda = mp; g.B = Pk + ms; g.ldb = mp; g.C = R->chol->L + (size_t) ms * mp + ms; g.ldc = mp;
+            g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+            g.bc_nb = nb; g.bc_stride = P * nb;
+            HD_CALL(hd_gemm_nt(R->st, g));
+        }
+    }
+    // ---- finish: transposed leaves, info -----------------------------------------------------------------------------
+    int info = 0, err = 0;
+    for (int i = 0; i < d->nlocal; ++i) {
+        DistRank *R = d->local[i];
+        HD_CUDA(cudaSetDevice(R->dev));
+        HD_CALL(hd_chol_finish(R->st, R->chol));
+        HD_CUDA(cudaMemcpyAsync(R->chol->hinfo, R->chol->dinfo, sizeof(int), cudaMemcpyDeviceToHost, R->st));
+        HD_CUDA(cudaMemcpyAsync(R->h_ctrl, R->ctrl, sizeof(int) * (4 * P + 1), cudaMemcpyDeviceToHost, R->st));
+    }
+    for (int i = 0; i < d->nlocal; ++i) {
+        DistRank *R = d->local[i];
+        HD_CUDA(cudaSetDevice(R->dev));
+        HD_CUDA(cudaStreamSynchronize(R->st));
+        HD_CUDA(cudaStreamSynchronize(R->push)); // our panels have left before the caller may touch L again
+        auto take = [&](int v) { if (v > 0 && v <= d->n && (info == 0 || v < info)) info = v; };
+        take(*R->chol->hinfo);
+        for (int q = 0; q < P; ++q)
+            if (q != R->rank && !R->peer[q].local) take(R->h_ctrl[2 * P + q]);
+        if (R->h_ctrl[4 * P]) err = 1;
+    }
+    for (int i = 0; i < d->nlocal; ++i) d->local[i]->chol->factored = (info == 0 && !err);
+    if (d->nlocal > 0) HD_CUDA(cudaSetDevice(d->local[0]->dev));
+    if (info_out) *info_out = info;
+    if (err) {
+        fprintf(stderr, "[hdsdpcu] dist_factor: timed out waiting for a peer\n");
+        return HD_FAILED;
+    }
+    return HD_OK;
+}
+
+// all-gather of up to 8 doubles per rank across processes (used for HKKTRegularize's global min of diag(M)).
+// d_out[q * cnt + t] = value t of rank q.  Only for ranks living in different processes.
+int dist_allgather_small(DistChol *d, const double *d_val, int cnt, double *d_out) {
+    if (!d->connected || d->nlocal != 1 || cnt > MAIL_CNT) return HD_FAILED;
+    DistRank *R = d->local[0];
+    const int P = d->P, seq = ++d->mail_seq;
+    MailDst dst{};
+    for (int q = 0; q < P; ++q) {
+        if (q == R->rank) continue;
+        char *c = R->peer[q].ctrl;
+        dst.mail[dst.n] = (double *) (c + MAIL_OFF) + (size_t) (seq & 1) * MAXP * MAIL_CNT + (size_t) R->rank * MAIL_CNT;
+        dst.flag[dst.n] = ctrl_ints(c) + 3 * P + R->rank;
+        ++dst.n;
+    }
+    HDK(mail_publish_kernel)<<<1, 32, 0, R->st>>>(dst, d_val, cnt, seq);
+    HDK(mail_collect_kernel)<<<1, 32, 0, R->st>>>(R->ctrl, P, R->rank, seq, d_val, cnt, d_out, ctrl_ints(R->ctrl) + 4 * P);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}

@@ -80,7 +80,15 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
     extern __shared__ __align__(16) double smem[];
     int tm, tn;
     if (!map_tile<BN>(tmap, blockIdx.x, tm, tn)) return;
-    const int m0 = tm * BM, n0 = tn * BN;
+    const int m0 = tm * BM;
+    int n0 = tn * BN;
+    if (g.bc_nb > 0) {
+        // block-cyclic N: local column block -> global column block (stride = nRanks * nb); tiles above the diagonal
+        // (and past the matrix edge, which lies above it) have no work
+        const int jb = n0 / g.bc_nb;
+        n0 = jb * g.bc_stride + (n0 - jb * g.bc_nb);
+        if ((g.flags & HD_GEMM_LOWER) && n0 > m0 + BM - 1) return;
+    }
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -233,11 +241,13 @@ template <int BN, int BK, int STAGES> constexpr int smem_bytes() { return STAGES
 
 template <int BN, int BK, int STAGES, int MINB>
 int launch_variant(cudaStream_t st, const GemmArgs &g) {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0; // one bit per device (function attributes are per context)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr >> (dev & 63) & 1ull)) {
         HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smem_bytes<BN, BK, STAGES>()));
-        attr = true;
+        attr |= 1ull << (dev & 63);
     }
     constexpr int GN = GROUP * (128 / BN);
     TileMap tmap;
@@ -245,6 +255,10 @@ int launch_variant(cudaStream_t st, const GemmArgs &g) {
     tmap.tiles_n = g.N / BN;
     tmap.lower = (g.flags & HD_GEMM_LOWER) ? 1 : 0;
     long nsuper;
+    if (g.bc_nb > 0) {
+        if (g.bc_nb % BM || g.bc_stride % g.bc_nb) return HD_FAILED;
+        tmap.lower = 0; // rectangular enumeration of the owned blocks; the kernel drops tiles above the diagonal
+    }
     if (tmap.lower) {
         if (g.M != g.N) return HD_FAILED;
         long s = (tmap.tiles_m + GROUP - 1) / GROUP;

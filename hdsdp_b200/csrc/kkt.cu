@@ -15,10 +15,11 @@
 
 namespace {
 
-__global__ void min_diag_kernel(const double *__restrict__ M, long ld, int m, double *out) {
+__global__ void min_diag_kernel(const double *__restrict__ M, long ld, int m, double *out, int rank, int nranks, int nb) {
     __shared__ double red[256];
     double v = 1e300;
-    for (int i = threadIdx.x; i < m; i += 256) v = fmin(v, M[(long) i * ld + i]);
+    for (int i = threadIdx.x; i < m; i += 256)
+        if (nranks <= 1 || (i / nb) % nranks == rank) v = fmin(v, M[(long) i * ld + i]); // only owned columns are assembled
     red[threadIdx.x] = v;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -36,6 +37,23 @@ __global__ void regularize_kernel(double *M, long ld, int m, double reg, const d
     r = fmin(r, 1e-05);
     if (r < 1e-14) r = 0.0;
     M[(long) i * ld + i] += r;
+}
+
+__global__ void min_vec_kernel(const double *__restrict__ v, int n, double *out) {
+    if (threadIdx.x == 0) {
+        double r = v[0];
+        for (int i = 1; i < n; ++i) r = fmin(r, v[i]);
+        *out = r;
+    }
+}
+
+// copy the lower trapezoids of the block columns owned by this rank (rows >= the block's first row)
+__global__ void copy_owned_kernel(double *__restrict__ dst, const double *__restrict__ src, long ld, int mp, int nb, int rank, int nranks) {
+    const int col = blockIdx.y;
+    if ((col / nb) % nranks != rank) return;
+    const int r0 = (col / nb) * nb;
+    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < mp; r += gridDim.x * blockDim.x)
+        dst[(long) col * ld + r] = src[(long) col * ld + r];
 }
 
 __global__ void add_diag_vec_kernel(double *M, long ld, int m, const double *__restrict__ d) {
@@ -115,6 +133,8 @@ void kkt_destroy(KktCU *k) {
     cudaFree(k->d_M); cudaFree(k->d_asinv); cudaFree(k->d_asinvrd); cudaFree(k->d_asinvc);
     cudaFree(k->d_scal); cudaFree(k->d_rhs);
     cudaFreeHost(k->h_scal); cudaFreeHost(k->h_vec);
+    if (k->dist) dist_destroy(k->dist);
+    if (k->d_gather) cudaFree(k->d_gather);
     chol_destroy(k->chol);
     delete k;
 }
@@ -144,7 +164,12 @@ int kkt_build_up(KktCU *k, int typeKKT) {
 
 int kkt_regularize(KktCU *k, double reg) {
     cudaStream_t st = hd_stream();
-    HDK(min_diag_kernel)<<<1, 256, 0, st>>>(k->d_M, k->mp, k->m, k->d_scal + 4);
+    HDK(min_diag_kernel)<<<1, 256, 0, st>>>(k->d_M, k->mp, k->m, k->d_scal + 4, k->rank, k->nranks, k->shard_nb);
+    if (k->dist && k->nranks > 1) {
+        // global min of diag(M) over the ranks' column shards (peer-memory all-gather of one double, dist.cu)
+        HD_CALL(dist_allgather_small(k->dist, k->d_scal + 4, 1, k->d_gather));
+        HDK(min_vec_kernel)<<<1, 32, 0, st>>>(k->d_gather, k->nranks, k->d_scal + 4);
+    }
     HDK(regularize_kernel)<<<nblk(k->m, 256), 256, 0, st>>>(k->d_M, k->mp, k->m, reg, k->d_scal + 4);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
@@ -215,6 +240,17 @@ int kkt_export(KktCU *k, double *asinv, double *asinvrd, double *asinvc, double 
 // (the reference would fall back to dsytrf LDL here, hdsdp_linsolver.c:2036-2039; not built yet)
 int kkt_factorize(KktCU *k, int *info_out) {
     cudaStream_t st = hd_stream();
+    if (k->dist && k->nranks > 1) {
+        // multi-GPU: this rank's block columns of M go into the factor buffer, the peers' columns arrive as factor panels
+        HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
+        HD_CUDA(cudaGetLastError());
+        HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
+        int info = 0;
+        int rc = dist_factor(k->dist, &info);
+        if (info_out) *info_out = info;
+        k->factored = (rc == HD_OK && info == 0);
+        return k->factored ? HD_OK : HD_FAILED;
+    }
     HD_CUDA(cudaMemcpyAsync(k->chol->L, k->d_M, sizeof(double) * (size_t) k->mp * k->mp, cudaMemcpyDeviceToDevice, st));
     HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
     int info = 0;

@@ -155,6 +155,26 @@ int     hdsdpcu_kkt_solve_dev(void *kkt, int nRhs, double *d_x /* stride padded 
 int  hdsdpcu_kkt_setshard(void *kkt, int rank, int nRanks);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU Schur matrix (replaces the single dpotrf of HKKTFactorize, interface/hdsdp_schur.c:328,
+ * linalg/hdsdp_linsolver.c:1096, when one process per GPU runs the solver).  M is distributed 1-D block-cyclic by
+ * block columns of width blockSize: rank r assembles and factors the columns c with (c / blockSize) % nRanks == r;
+ * finished factor panels are copied into the peers' buffers over NVLink peer memory (CUDA IPC), so after
+ * hdsdpcu_kkt_factorize every rank holds the complete factor and hdsdpcu_kkt_solve needs no communication.
+ *   1. every rank: hdsdpcu_kkt_dist_init, hdsdpcu_kkt_dist_export -> blob of hdsdpcu_dist_blob_bytes() bytes
+ *   2. the host program all-gathers the blobs in rank order (MPI_Allgather, torch.distributed, a file ...)
+ *   3. every rank: hdsdpcu_kkt_dist_connect(all blobs)
+ * buildup / regularize / factorize / solve are then called in lock step by all ranks with the same arguments;
+ * the side vectors (hdsdpcu_kkt_export) are complete on every rank, hdsdpcu_kkt_getmatrix returns the owned columns.
+ * ------------------------------------------------------------------------------------------- */
+int  hdsdpcu_dist_blob_bytes(void);
+int  hdsdpcu_dist_owner(int col, int blockSize, int nRanks);   /* pure host arithmetic, no device needed */
+int  hdsdpcu_kkt_dist_init(void *kkt, int rank, int nRanks, int blockSize);
+int  hdsdpcu_kkt_dist_export(void *kkt, void *blob);
+int  hdsdpcu_kkt_dist_connect(void *kkt, const void *blobs /* nRanks blobs, rank order */);
+/* test hook: the same schedule with nRanks ranks inside this process on one GPU (events instead of peer flags) */
+int  hdsdpcu_distchol_selftest(int n, int blockSize, int nRanks, const double *A, double *outL0, double *outLlast, int *info);
+
+/* ---------------------------------------------------------------------------------------------
  * Stand-alone kernels exposed for tests and roofline measurement
  * ------------------------------------------------------------------------------------------- */
 /* C (M x N) = alpha A (M x K) B(N x K)^T + beta C on device pointers; M,N % 128 == 0, K % 16 == 0 */

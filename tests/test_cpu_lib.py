@@ -92,3 +92,16 @@ def test_theta_bench_point_is_interior():
     c.set_resi(bench.RD)
     ok, _ = c.set_point(y, bench.TAU)
     assert ok
+
+
+def test_block_cyclic_ownership_arithmetic():
+    """hdsdpcu_dist_owner is the single definition of which rank assembles / factors a Schur column (pure host)."""
+    from hdsdp_b200 import _lib
+    lib = _lib.lib()
+    assert lib.hdsdpcu_dist_blob_bytes() == 192
+    for nb, P in ((128, 2), (512, 8), (256, 3)):
+        cols = np.arange(0, 5000, 37)
+        got = np.array([lib.hdsdpcu_dist_owner(int(c), nb, P) for c in cols])
+        assert np.array_equal(got, (cols // nb) % P)
+        counts = np.bincount((np.arange(50048) // nb) % P, minlength=P)
+        assert counts.max() - counts.min() <= nb   # block-cyclic balance
