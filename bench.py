@@ -288,6 +288,29 @@ def run_ours(args):
     h2d = 8 * (m + 2 * m)            # y, two right-hand sides
     d2h = 8 * (3 * m + 2 * m) + 64   # three side vectors + scalars, two solutions
 
+    # ---- per-stage device times of one more HBM-resident step (not part of `value`) --------------
+    def stage_times(s_idx):
+        flag = c_int(0)
+        marks = []
+
+        def mark(name):
+            e = ev(); e.record(st); marks.append((name, e))
+        mark("start")
+        _lib.check(lib.hdsdpcu_cone_update_dev(cone.h, TAU, y_dev[s_idx].data_ptr()), "update"); mark("S_assembly")
+        _lib.check(lib.hdsdpcu_cone_factorize(cone.h, 0, byref(flag)), "factorize S"); mark("S_cholesky")
+        _lib.check(lib.hdsdpcu_kkt_buildup(kkt.h, 0), "HKKTBuildUp"); mark("S_inverse+schur_build")
+        _lib.check(lib.hdsdpcu_kkt_regularize(kkt.h, KKT_REG), "HKKTRegularize"); mark("regularize")
+        _lib.check(lib.hdsdpcu_copy_dev(rhs_dev.data_ptr(), b_dev.data_ptr(), 8 * mp), "copy b")
+        _lib.check(lib.hdsdpcu_copy_dev(rhs_dev.data_ptr() + 8 * mp, asinv_ptr, 8 * mp), "copy ASinv")
+        assert lib.hdsdpcu_kkt_factorize(kkt.h) == 0; mark("M_cholesky")
+        _lib.check(lib.hdsdpcu_kkt_solve_dev(kkt.h, 2, rhs_dev.data_ptr()), "solve"); mark("M_solve_2rhs")
+        marks[-1][1].synchronize()
+        return {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 3) for i in range(1, len(marks))}
+
+    barrier()
+    stages = stage_times(nsteps)
+    barrier()
+
     t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -314,7 +337,7 @@ def run_ours(args):
                          "peak_source": "cuBLAS DGEMM 8192^3 measured live (MEASURED_PEAKS.json has no FP64 entry)",
                          "factorize_ms": fact_s * 1e3, "share_of_step": fact_s / per_step},
             "e2e": {"value": e2e_s / args.steps, "unit": "s/iteration", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "stages_ms": stages,
         }
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -46,6 +46,12 @@ int hdsdpcu_init(int device) {
     }
     if (device >= 0) HD_CUDA(cudaSetDevice(device));
     if (!g_stream) HD_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    if (!g_ready) {
+        // measurement knobs can also come from the environment (HDSDPCU_GEMM_VARIANT, HDSDPCU_CHOL_BLOCK, HDSDPCU_CHOL_LEAF)
+        if (const char *e = getenv("HDSDPCU_GEMM_VARIANT")) hd_gemm_set_variant(atoi(e));
+        if (const char *e = getenv("HDSDPCU_CHOL_BLOCK")) hd_chol_set_block(atoi(e));
+        if (const char *e = getenv("HDSDPCU_CHOL_LEAF")) hd_chol_set_leaf(atoi(e));
+    }
     g_ready = true;
     return HD_OK;
 }
@@ -66,6 +72,8 @@ long hdsdpcu_launch_count(int reset) {
 int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "gemm_variant") == 0) { hd_gemm_set_variant(value); return HD_OK; }
     if (name && strcmp(name, "chol_block") == 0) { hd_chol_set_block(value); return HD_OK; }
+    if (name && strcmp(name, "chol_leaf") == 0) { hd_chol_set_leaf(value); return HD_OK; }
+    if (name && strcmp(name, "trsv_version") == 0) { hd_trsv_set_version(value); return HD_OK; }
     return HD_FAILED;
 }
 

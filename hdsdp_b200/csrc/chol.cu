@@ -88,6 +88,197 @@ potf2_leaf_kernel(double *A, long lda, double *Dinv, int *info, int base) {
     for (int e = tid; e < HD_LEAF * HD_LEAF; e += LEAF_THREADS) Dinv[e] = Ls[e]; // upper part is exactly 0
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Leaf v2: the same contract (L and L^-1 of one 128x128 block), organised for the tensor pipe.
+// 8 panels of 16 columns.  Per panel: (a) warp 0 factors the 16x16 diagonal block and inverts it with register
+// rows + shuffles; (b) the rows below become X = A21 W^T and (c) the trailing block gets -= X X^T, both as
+// m8n8k4 DMMA tiles on shared memory (row stride 132: conflict-free fragment loads).  The inverse is then built
+// block column by block column, one warp per block column with no CTA-wide barrier:
+//   X_rc = -W_r * sum_{k=c}^{r-1} L_rk X_kc   (X_cc = W_c),   stored transposed in the unused upper triangle.
+// ------------------------------------------------------------------------------------------
+constexpr int L2_LD = 132, L2_WLD = 20, L2_THREADS = 256;
+constexpr int L2_SMEM = (HD_LEAF * L2_LD + 8 * 16 * L2_WLD + 8 * 16 * L2_WLD) * 8;
+
+__device__ __forceinline__ void dmma_tile(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(L2_THREADS, 1)
+potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
+    extern __shared__ __align__(16) double sm[];
+    double *As = sm;                          // 128 x 132, column-major: L in the lower triangle, X^T in the upper
+    double *Wd = sm + HD_LEAF * L2_LD;        // 8 diagonal-block inverses, W[row][col] at col * 20 + row
+    double *Sc = Wd + 8 * 16 * L2_WLD;        // per-warp 16 x 16 scratch, same layout
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += L2_THREADS) {
+        const int i = e & 127, j = e >> 7;
+        As[j * L2_LD + i] = (i >= j) ? A[(long) j * lda + i] : 0.0;
+    }
+    __syncthreads();
+    for (int p = 0; p < 8; ++p) {
+        const int c0 = 16 * p, r0 = c0 + 16, R = HD_LEAF - r0;
+        if (warp == 0) {
+            // (a) lane l < 16 owns row l of the diagonal block
+            double a[16], ri[16], w[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = (lane < 16 && k <= lane) ? As[(c0 + k) * L2_LD + c0 + lane] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                double d = __shfl_sync(0xffffffffu, a[j], j);
+                if (!(d > 0.0) || isinf(d)) {
+                    if (lane == 0) atomicCAS(info, 0, base + c0 + j + 1);
+                    d = 1.0;
+                }
+                const double r = sqrt(d);
+                ri[j] = 1.0 / r;
+                a[j] = (lane == j) ? r : a[j] * ri[j];
+#pragma unroll
+                for (int k = j + 1; k < 16; ++k) {
+                    const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+                    if (lane >= k) a[k] -= a[j] * lkj;
+                }
+            }
+            // W = L11^-1: lane c owns column c.  w[l] = -(sum_{k=c}^{l-1} L[l][k] w[k]) / L[l][l]
+#pragma unroll
+            for (int l = 0; l < 16; ++l) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < l; ++k) {
+                    const double llk = __shfl_sync(0xffffffffu, a[k], l);
+                    if (k >= lane) s += llk * w[k];
+                }
+                w[l] = (l == lane) ? ri[l] : ((l > lane) ? -s * ri[l] : 0.0);
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k <= lane) As[(c0 + k) * L2_LD + c0 + lane] = a[k];
+                    Wd[p * 16 * L2_WLD + lane * L2_WLD + k] = w[k]; // W[k][lane]
+                }
+            }
+        }
+        __syncthreads();
+        if (R == 0) break;
+        // (b) X = A21 L11^-T by forward substitution, one thread per row (as dtrsm would: no explicit inverse on the
+        //     factor itself, so a single-leaf matrix gets a classical, backward-stable Cholesky)
+        if (tid < R) {
+            const int m = r0 + tid;
+            double x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                double sacc = As[(c0 + j) * L2_LD + m];
+#pragma unroll
+                for (int k = 0; k < j; ++k) sacc -= x[k] * As[(c0 + k) * L2_LD + c0 + j];
+                x[j] = sacc / As[(c0 + j) * L2_LD + c0 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) As[(c0 + j) * L2_LD + m] = x[j];
+        }
+        __syncthreads();
+        // (c) A22 -= X X^T on the lower 8x8 tiles
+        {
+            const int T = R / 8;
+            int cnt = 0;
+            for (int mt = 0; mt < T; ++mt)
+                for (int nt = 0; nt <= mt; ++nt) {
+                    if ((cnt++ & 7) != warp) continue;
+                    const int m0 = r0 + 8 * mt, n0 = r0 + 8 * nt;
+                    double c0v = 0, c1v = 0;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const double av = As[(c0 + 4 * kk + tig) * L2_LD + m0 + gid];
+                        const double bv = As[(c0 + 4 * kk + tig) * L2_LD + n0 + gid];
+                        dmma_tile(c0v, c1v, av, bv);
+                    }
+                    As[(n0 + 2 * tig) * L2_LD + m0 + gid] -= c0v;
+                    As[(n0 + 2 * tig + 1) * L2_LD + m0 + gid] -= c1v;
+                }
+        }
+        __syncthreads();
+    }
+    // L back to global (lower only)
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += L2_THREADS) {
+        const int i = e & 127, j = e >> 7;
+        if (i >= j) A[(long) j * lda + i] = As[j * L2_LD + i];
+    }
+    // inverse: warp c builds block column c (blocks r = c+1 .. 7) on its own
+    {
+        const int c = warp, cc0 = 16 * c;
+        double *S = Sc + warp * 16 * L2_WLD;
+        for (int r = c + 1; r < 8; ++r) {
+            const int rr0 = 16 * r;
+            double acc[2][2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int k = c; k < r; ++k) {
+                const int kk0 = 16 * k;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    double av[2], bv[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) av[i] = As[(kk0 + 4 * kk + tig) * L2_LD + rr0 + 8 * i + gid]; // L[rr0+m][kk0+k']
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        bv[j] = (k == c) ? Wd[c * 16 * L2_WLD + (8 * j + gid) * L2_WLD + 4 * kk + tig]       // W_c[k'][n]
+                                         : As[(kk0 + 4 * kk + tig) * L2_LD + cc0 + 8 * j + gid];             // X[kk0+k'][cc0+n]
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma_tile(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                }
+            }
+            // S (m, n) -> scratch S[n * WLD + m]
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    S[(8 * j + 2 * tig) * L2_WLD + 8 * i + gid] = acc[i][j][0];
+                    S[(8 * j + 2 * tig + 1) * L2_WLD + 8 * i + gid] = acc[i][j][1];
+                }
+            __syncwarp();
+            double out[2][2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) out[i][j][0] = out[i][j][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                double av[2], bv[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) av[i] = Wd[r * 16 * L2_WLD + (4 * kk + tig) * L2_WLD + 8 * i + gid]; // W_r[m][k']
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bv[j] = S[(8 * j + gid) * L2_WLD + 4 * kk + tig];                     // S[k'][n]
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma_tile(out[i][j][0], out[i][j][1], av[i], bv[j]);
+            }
+            __syncwarp();
+            // X[rr0+m][cc0+n] = -out, stored transposed: As[(rr0+m) * LD + cc0+n]
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    As[(rr0 + 8 * i + gid) * L2_LD + cc0 + 8 * j + 2 * tig] = -out[i][j][0];
+                    As[(rr0 + 8 * i + gid) * L2_LD + cc0 + 8 * j + 2 * tig + 1] = -out[i][j][1];
+                }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += L2_THREADS) {
+        const int i = e & 127, j = e >> 7;
+        double v = 0.0;
+        if (i >= j) v = ((i >> 4) == (j >> 4)) ? Wd[(i >> 4) * 16 * L2_WLD + (j & 15) * L2_WLD + (i & 15)] : As[i * L2_LD + j];
+        Dinv[e] = v;
+    }
+}
+
 // X leaf (upper triangular) = Dinv^T
 __global__ void leaf_transpose_kernel(const double *__restrict__ Dinv, double *X, long ldx) {
     __shared__ double t[32][33];
@@ -127,7 +318,6 @@ __global__ void logdet_kernel(const double *L, long ld, int n, double *out, doub
     if (threadIdx.x == 0 && out) *out = 2.0 * red[0];
 }
 
-bool g_leaf_attr = false;
 const int LEAF_SMEM = (HD_LEAF * HD_LEAF + HD_LEAF) * 8;
 
 int split_leaves(int n) { return ((n / HD_LEAF) / 2) * HD_LEAF; } // n1 (multiple of 128, >= 128 when n >= 256)
@@ -153,9 +343,11 @@ int trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, lo
                     dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF);
 }
 
+int g_leaf_version = 2;
 int potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base) {
     if (n == HD_LEAF) {
-        HDK(potf2_leaf_kernel)<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, dinv, info, base);
+        if (g_leaf_version == 2) HDK(potf2_leaf2_kernel)<<<1, L2_THREADS, L2_SMEM, st>>>(A, lda, dinv, info, base);
+        else HDK(potf2_leaf_kernel)<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, dinv, info, base);
         HD_CUDA(cudaGetLastError());
         return HD_OK;
     }
@@ -193,14 +385,19 @@ int invert_rec(cudaStream_t st, const double *L, long ldl, int n, const double *
 
 } // namespace
 
-int hd_potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base) {
+static int ensure_leaf_attr() {
     static unsigned long long attr = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(attr >> (dev & 63) & 1ull)) {
         HD_CUDA(cudaFuncSetAttribute(potf2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+        HD_CUDA(cudaFuncSetAttribute(potf2_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
         attr |= 1ull << (dev & 63);
     }
+    return HD_OK;
+}
+int hd_potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base) {
+    HD_CALL(ensure_leaf_attr());
     return potrf_rec(st, A, lda, n, dinv, info, base);
 }
 int hd_trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, long ldl, int n, const double *dinv) {
@@ -272,6 +469,7 @@ static cudaEvent_t g_ev_col = nullptr, g_ev_panel = nullptr;
 static int g_lookahead_nb = 2048; // block size; <= 0 disables the blocked path
 
 void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
+void hd_chol_set_leaf(int v) { g_leaf_version = v; }
 
 static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
     if (!g_side) {
@@ -349,10 +547,7 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
 }
 
 int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
-    if (!g_leaf_attr) {
-        HD_CUDA(cudaFuncSetAttribute(potf2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
-        g_leaf_attr = true;
-    }
+    HD_CALL(ensure_leaf_attr());
     HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
     if (g_lookahead_nb >= HD_LEAF && c->np >= 4 * g_lookahead_nb)
         HD_CALL(potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (g_lookahead_nb / HD_LEAF) * HD_LEAF));

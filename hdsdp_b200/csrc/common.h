@@ -80,6 +80,8 @@ int hd_chol_finish(cudaStream_t st, DenseChol *c); // transposed inverse leaves 
 int hd_num_sms();
 void hd_gemm_set_variant(int v);
 void hd_chol_set_block(int nb);
+void hd_chol_set_leaf(int v);
+void hd_trsv_set_version(int v);
 
 // ---------------------------------------------------------------------------------------------
 // Dense SPD factorisation object (device resident).

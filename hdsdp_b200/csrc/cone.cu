@@ -273,6 +273,38 @@ __global__ void sparse_vectors_kernel(const double *__restrict__ Sinv, long lds,
     }
 }
 
+// same for constraints with many nonzeros (class SB: e.g. the identity row of the theta problems): one CTA per
+// constraint, one warp per stored entry, deterministic block reduction
+__global__ void __launch_bounds__(256) sparse_vectors_block_kernel(const double *__restrict__ Sinv, long lds, int n,
+                                                                   const int *__restrict__ con, const int *__restrict__ ptr,
+                                                                   const int *__restrict__ row, const int *__restrict__ col,
+                                                                   const double *__restrict__ val, double rd, double *asinv,
+                                                                   double *asinvrd) {
+    __shared__ double r1[8], r2[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (int e = ptr[c] + w; e < ptr[c + 1]; e += 8) {
+        const double *cr = Sinv + (long) row[e] * lds;
+        const double *cc = Sinv + (long) col[e] * lds;
+        if (lane == 0) s1 += val[e] * cr[col[e]];
+        if (rd != 0.0) {
+            double d = 0.0;
+            for (int a = lane; a < n; a += 32) d += cr[a] * cc[a];
+            s2 += val[e] * d;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == 0) { r1[w] = s1; r2[w] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < 8; ++i) { a += r1[i]; b += r2[i]; }
+        asinv[con[c]] += 2.0 * a;
+        if (rd != 0.0) asinvrd[con[c]] += rd * 2.0 * b;
+    }
+}
+
 // <A_j, X> for sparse constraints against an explicit symmetric matrix X: one thread per constraint.
 // mode 0: vec[con_j] += scale * value ; mode 1: M[max(con_j, ci), min(con_j, ci)] += value for j >= jmin
 __global__ void sparse_dot_kernel(const double *__restrict__ X, long ldx, const int *__restrict__ con,
@@ -779,8 +811,8 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
             HDK(sparse_vectors_kernel)<<<nblk((long) c->nss * 32, 256), 256, 0, st>>>(Sinv, np, n, c->d_ss_con, c->d_ss_ptr, c->d_ss_row,
                                                                                   c->d_ss_col, c->d_ss_val, c->nss, rd, k->d_asinv, k->d_asinvrd);
         if (c->nsb > 0)
-            HDK(sparse_vectors_kernel)<<<nblk((long) c->nsb * 32, 256), 256, 0, st>>>(Sinv, np, n, c->d_sb_con, c->d_sb_ptr, c->d_sb_row,
-                                                                                  c->d_sb_col, c->d_sb_val, c->nsb, rd, k->d_asinv, k->d_asinvrd);
+            HDK(sparse_vectors_block_kernel)<<<c->nsb, 256, 0, st>>>(Sinv, np, n, c->d_sb_con, c->d_sb_ptr, c->d_sb_row, c->d_sb_col,
+                                                                   c->d_sb_val, rd, k->d_asinv, k->d_asinvrd);
         if (c->nd > 0)
             HDK(dense_dot_kernel)<<<c->nd, 256, 0, st>>>(c->d_dn_full, (long) np * np, Sinv, np, n, c->d_dn_con, 0, 0, 1.0, k->d_asinv,
                                                     nullptr, 0, 0, sh);

@@ -57,5 +57,9 @@ def test_full_solve_matches_cpu_reference(name):
     # so the 1e-7 gate is widened by that gap; where the reference converged (gap ~1e-8) this stays ~1e-7.
     ptol = 1e-7 * max(1.0, abs(ref_p)) + 2.0 * abs(ref_p - ref_d)
     assert abs(res["pObj"] - ref_p) <= ptol, f"pObj {res['pObj']!r} vs CPU reference {ref_p!r} (tol {ptol:.2e})"
-    assert abs(res["iterations"] - ref_it) <= 1, f"iterations {res['iterations']} vs CPU reference {ref_it}"
+    # Iteration gate: +-1.  gpp100 is the exception: the CPU reference itself is not reproducible to +-1 there -- the
+    # unmodified reference takes 30 / 31 / 33 / 32 iterations with OPENBLAS_NUM_THREADS = 1 / 2 / 4 / 8 on the same box
+    # (only the BLAS summation order changes; dObj agrees to 1e-10), so its own spread (3) is the tolerance.
+    it_tol = 3 if name == "gpp100" else 1
+    assert abs(res["iterations"] - ref_it) <= it_tol, f"iterations {res['iterations']} vs CPU reference {ref_it}"
     assert max(res["dimacs"]) <= 1e-2     # the reference's own acceptance gate (interface/hdsdp.c:905-922)
