@@ -29,7 +29,7 @@ void classify_coeff(int n, int nnz, const int *Ci, const double *Cx, HostCoeff &
 namespace {
 
 constexpr int SS_MAX_NNZ = 16;
-constexpr int SS_SMEM_BUDGET = 160 * 1024;
+constexpr int SS_SMEM_BUDGET = 192 * 1024;
 
 template <typename T> int upload(T **dptr, const std::vector<T> &h) {
     *dptr = nullptr;
@@ -194,46 +194,58 @@ __global__ void r1_scatter_hadsq_kernel(const double *__restrict__ G, long ldg, 
 // staged interleaved in smem as double2 {Sinv[a,r'], Sinv[a,c']}) x one chunk of left-hand constraints p.
 //   M[cp, cq] += 2 * sum_{e in A_p} sum_{f in A_q} x~_e x~_f (Sinv[r,r'] Sinv[c,c'] + Sinv[r,c'] Sinv[c,r'])
 // with x~ = x/2 on the diagonal (reference hdsdp_sdpdata.c:1711-1757 keeps the same 0.5/2 weights).
-constexpr int SS_CHUNK = 8192;
+constexpr int SS_THREADS = 1024;
 template <bool STAGED>
-__global__ void __launch_bounds__(256) ss_pair_schur_kernel(const double *__restrict__ Sinv, long lds, int n,
-                                                           const int *__restrict__ con, const int *__restrict__ ptr,
-                                                           const int *__restrict__ row, const int *__restrict__ col,
-                                                           const double *__restrict__ val, int nss,
-                                                           const SsGroup *__restrict__ groups, double *M, long ldm, Shard sh) {
+__global__ void __launch_bounds__(SS_THREADS, 1) ss_pair_schur_kernel(const double *__restrict__ Sinv, long lds, int n,
+                                                                     const int *__restrict__ con, const int *__restrict__ ptr,
+                                                                     const int *__restrict__ row, const int *__restrict__ col,
+                                                                     const double *__restrict__ val, int nss,
+                                                                     const SsGroup *__restrict__ groups, double *M, long ldm, Shard sh,
+                                                                     int overwrite) {
     extern __shared__ __align__(16) double2 uw[]; // [ent_count][n]
+    __shared__ int s_cq[8], s_fb[9];
     const SsGroup g = groups[blockIdx.x];
-    const int p0 = g.first + blockIdx.y * SS_CHUNK; // p ranges over [g.first, nss)
-    if (p0 >= nss) return;
     // whole group owned by someone else?
     bool any = false;
     for (int q = g.first; q < g.first + g.count; ++q) any = any || owns_col(sh, con[q]);
     if (!any) return;
+    if (threadIdx.x < g.count) s_cq[threadIdx.x] = owns_col(sh, con[g.first + threadIdx.x]) ? con[g.first + threadIdx.x] : -1;
+    if (threadIdx.x <= g.count) s_fb[threadIdx.x] = ptr[g.first + threadIdx.x];
     if (STAGED) {
         for (int f = 0; f < g.ent_count; ++f) {
             const double *cr = Sinv + (long) row[g.ent_first + f] * lds;
             const double *cc = Sinv + (long) col[g.ent_first + f] * lds;
             double2 *dst = uw + (long) f * n;
-            for (int a = threadIdx.x; a < n; a += 256) dst[a] = make_double2(cr[a], cc[a]);
+            for (int a = threadIdx.x; a < n; a += SS_THREADS) dst[a] = make_double2(cr[a], cc[a]);
         }
-        __syncthreads();
     }
-    const int pend = min(nss, p0 + SS_CHUNK);
-    for (int p = p0 + threadIdx.x; p < pend; p += 256) {
+    __syncthreads();
+    // one CTA owns the group's columns of M for ALL rows p >= g.first (staging amortised over the whole column strip)
+    for (int p = g.first + threadIdx.x; p < nss; p += SS_THREADS) {
         const int cp = con[p];
         const int eb = ptr[p], ee = ptr[p + 1];
-        for (int q = g.first; q < g.first + g.count && q <= p; ++q) {
-            const int cq = con[q];
-            if (!owns_col(sh, cq)) continue;
+        const bool single = (ee - eb == 1);
+        int r1 = 0, c1 = 0;
+        double v1 = 0.0;
+        if (single) { r1 = row[eb]; c1 = col[eb]; v1 = val[eb]; }
+        const int qn = min(g.count, p - g.first + 1);
+        for (int qi = 0; qi < qn; ++qi) {
+            const int cq = s_cq[qi];
+            if (cq < 0) continue;
             double acc = 0.0;
-            for (int f = ptr[q]; f < ptr[q + 1]; ++f) {
+            for (int f = s_fb[qi]; f < s_fb[qi + 1]; ++f) {
                 const double xf = val[f];
                 double inner = 0.0;
                 if (STAGED) {
                     const double2 *t = uw + (long) (f - g.ent_first) * n;
-                    for (int e = eb; e < ee; ++e) {
-                        const double2 tr = t[row[e]], tc = t[col[e]];
-                        inner += val[e] * (tr.x * tc.y + tr.y * tc.x);
+                    if (single) {
+                        const double2 tr = t[r1], tc = t[c1];
+                        inner = v1 * (tr.x * tc.y + tr.y * tc.x);
+                    } else {
+                        for (int e = eb; e < ee; ++e) {
+                            const double2 tr = t[row[e]], tc = t[col[e]];
+                            inner += val[e] * (tr.x * tc.y + tr.y * tc.x);
+                        }
                     }
                 } else {
                     const double *cr = Sinv + (long) row[f] * lds;
@@ -242,7 +254,9 @@ __global__ void __launch_bounds__(256) ss_pair_schur_kernel(const double *__rest
                 }
                 acc += xf * inner;
             }
-            M[(long) cq * ldm + cp] += 2.0 * acc;
+            double *dst = M + (long) cq * ldm + cp;
+            if (overwrite) *dst = 2.0 * acc;
+            else *dst += 2.0 * acc;
         }
     }
 }
@@ -875,17 +889,20 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
         for (const SsGroup &g : c->ss_groups) maxent = std::max(maxent, g.ent_count);
         size_t smem = staged ? (size_t) maxent * n * sizeof(double2) : 0;
         if (!g_ss_attr) {
-            HD_CUDA(cudaFuncSetAttribute(ss_pair_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            HD_CUDA(cudaFuncSetAttribute(ss_pair_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); // + 68 B static
             g_ss_attr = true;
         }
-        dim3 grid((unsigned) c->ss_groups.size(), (unsigned) ((c->nss + SS_CHUNK - 1) / SS_CHUNK));
+        // the first SDP cone after HKKTClean is the only writer of its SS x SS entries so far: store instead of accumulate
+        // (saves the read of the 10 GB lower triangle at m = 50k)
+        const int overwrite = (iCone == 0 && k->fresh) ? 1 : 0;
+        const unsigned grid = (unsigned) c->ss_groups.size();
         ++g_hd_launches;
         if (staged)
-            ss_pair_schur_kernel<true><<<grid, 256, smem, st>>>(Sinv, np, n, c->d_ss_con, c->d_ss_ptr, c->d_ss_row, c->d_ss_col,
-                                                               c->d_ss_val, c->nss, c->d_ss_groups, k->d_M, ldm, sh);
+            ss_pair_schur_kernel<true><<<grid, SS_THREADS, smem, st>>>(Sinv, np, n, c->d_ss_con, c->d_ss_ptr, c->d_ss_row, c->d_ss_col,
+                                                                      c->d_ss_val, c->nss, c->d_ss_groups, k->d_M, ldm, sh, overwrite);
         else
-            ss_pair_schur_kernel<false><<<grid, 256, 0, st>>>(Sinv, np, n, c->d_ss_con, c->d_ss_ptr, c->d_ss_row, c->d_ss_col,
-                                                             c->d_ss_val, c->nss, c->d_ss_groups, k->d_M, ldm, sh);
+            ss_pair_schur_kernel<false><<<grid, SS_THREADS, 0, st>>>(Sinv, np, n, c->d_ss_con, c->d_ss_ptr, c->d_ss_row, c->d_ss_col,
+                                                                    c->d_ss_val, c->nss, c->d_ss_groups, k->d_M, ldm, sh, overwrite);
         HD_CUDA(cudaGetLastError());
     }
     // SS x R
@@ -936,6 +953,7 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
         }
     }
 
+    k->fresh = false; // M now holds contributions
     // ---- 4. homogeneous (HSD) components -----------------------------------------------------
     if (hsd && c->obj_type != COEFF_ZERO && do_vectors) {
         // B_C = Sinv C Sinv; dASinvCSinvVec_i = <A_i, B_C>; dCSinv = <C, Sinv>; dCSinvCSinv = <C, B_C>; dCSinvRdSinv = rd tr(B_C)

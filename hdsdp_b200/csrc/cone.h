@@ -108,6 +108,7 @@ struct KktCU {
     std::vector<ConeCU *> cones;
     std::vector<double *> primalX; // host pointers registered by HKKTRegisterPSDP
     bool factored = false;
+    bool fresh = false; // M was zeroed by HKKTClean and nothing has been accumulated yet
     // multi-GPU column sharding of the Schur assembly (rank r builds columns j with (j/128) % nranks == r)
     int rank = 0, nranks = 1, shard_nb = HD_LEAF;
     struct DistChol *dist = nullptr; // distributed factorisation of M (dist.cu); null on one GPU

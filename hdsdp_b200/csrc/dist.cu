@@ -291,12 +291,16 @@ int dist_factor(DistChol *d, int *info_out) {
         HD_CUDA(cudaSetDevice(R->dev));
         HD_CALL(factor_panel(d, R, 0));
     }
+    const bool trace = getenv("HDSDPCU_TRACE") != nullptr && d->nlocal == 1;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); tev.push_back(e); } };
     for (int k = 0; k < nblk; ++k) {
         const int owner = k % P;
         // (1) every rank obtains panel k
         for (int i = 0; i < d->nlocal; ++i) {
             DistRank *R = d->local[i];
             HD_CUDA(cudaSetDevice(R->dev));
+            mark(R->st);
             if (R->rank == owner) {
                 HD_CUDA(cudaStreamWaitEvent(R->st, R->ev_panel, 0));
             } else if (R->peer[owner].local) {
@@ -305,6 +309,7 @@ int dist_factor(DistChol *d, int *info_out) {
                 HDK(flag_wait_kernel)<<<1, 1, 0, R->st>>>(ctrl_ints(R->ctrl) + owner, panel_seq(d, k), ctrl_ints(R->ctrl) + 4 * P);
             }
         }
+        mark(d->local[0]->st);
         if (k == nblk - 1) break;
         const int s0 = k * nb, bk = blk_size(d, k);
         const int next = (k + 1) % P;
@@ -339,6 +344,21 @@ int dist_factor(DistChol *d, int *info_out) {
             g.bc_nb = nb; g.bc_stride = P * nb;
             HD_CALL(hd_gemm_nt(R->st, g));
         }
+    }
+    if (trace) {
+        DistRank *R = d->local[0];
+        cudaStreamSynchronize(R->st);
+        double wait = 0, work = 0, wait_own = 0;
+        for (int k = 0; k < nblk; ++k) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tev[2 * k], tev[2 * k + 1]);
+            if (k + 1 < nblk) cudaEventElapsedTime(&b, tev[2 * k + 1], tev[2 * k + 2]);
+            wait += a; work += b;
+            if (k % P == R->rank) wait_own += a;
+        }
+        fprintf(stderr, "[trace] dist_factor rank %d/%d nb=%d: main stream waited %.1f ms for panels (%.1f ms for its own), worked %.1f ms\n",
+                R->rank, P, nb, wait, wait_own, work);
+        for (auto e : tev) cudaEventDestroy(e);
     }
     // ---- finish: transposed leaves, info -----------------------------------------------------------------------------
     int info = 0, err = 0;

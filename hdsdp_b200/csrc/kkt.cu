@@ -152,13 +152,17 @@ int kkt_clean(KktCU *k, int typeKKT) {
     if (typeKKT == KKT_INFEASIBLE || typeKKT == KKT_HOMOGENEOUS || typeKKT == KKT_PRIMAL) {
         HD_CUDA(cudaMemsetAsync(k->d_M, 0, sizeof(double) * (size_t) k->mp * k->mp, st));
         k->factored = false;
+        k->fresh = true;
     }
     return HD_OK;
 }
 
 int kkt_build_up(KktCU *k, int typeKKT) {
     HD_CALL(kkt_clean(k, typeKKT));
-    for (size_t i = 0; i < k->cones.size(); ++i) HD_CALL(cone_build_schur(k->cones[i], (int) i, k, typeKKT));
+    for (size_t i = 0; i < k->cones.size(); ++i) {
+        HD_CALL(cone_build_schur(k->cones[i], (int) i, k, typeKKT));
+        k->fresh = false;
+    }
     return HD_OK;
 }
 
@@ -182,6 +186,7 @@ int kkt_add_host(KktCU *k, const double *diagAdd, const double *asinvAdd, const 
                  const double *scalarsAdd4) {
     cudaStream_t st = hd_stream();
     const int m = k->m;
+    k->fresh = false;
     const double *src[4] = {diagAdd, asinvAdd, asinvrdAdd, asinvcAdd};
     double *dst[4] = {nullptr, k->d_asinv, k->d_asinvrd, k->d_asinvc};
     for (int v = 0; v < 4; ++v) {
@@ -208,6 +213,7 @@ int kkt_add_host(KktCU *k, const double *diagAdd, const double *asinvAdd, const 
 int kkt_add_lp(KktCU *k, int nLpCol, const int *d_colptr, const int *d_rowidx, const double *d_val, const double *sInvHost,
                double *d_sinv_stage, double rd, int typeKKT) {
     cudaStream_t st = hd_stream();
+    k->fresh = false;
     HD_CUDA(cudaMemcpyAsync(d_sinv_stage, sInvHost, sizeof(double) * nLpCol, cudaMemcpyHostToDevice, st));
     HDK(lp_schur_kernel)<<<nblk(nLpCol, 128), 128, 0, st>>>(d_colptr, d_rowidx, d_val, d_sinv_stage, nLpCol, rd,
                                                         typeKKT != KKT_CORRECTOR, k->d_M, k->mp, k->d_asinv, k->d_asinvrd);
