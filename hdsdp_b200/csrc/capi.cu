@@ -77,6 +77,8 @@ int hdsdpcu_set_option(const char *name, int value) {
     return HD_FAILED;
 }
 
+int hdsdpcu_debug_leafclk(long long *out) { return hd_leaf_clocks(out); }
+
 int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes) {
     HD_CALL(ensure_ready());
     HD_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t) bytes, cudaMemcpyDeviceToDevice, g_stream));

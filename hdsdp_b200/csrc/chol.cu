@@ -98,7 +98,7 @@ potf2_leaf_kernel(double *A, long lda, double *Dinv, int *info, int base) {
 //   X_rc = -W_r * sum_{k=c}^{r-1} L_rk X_kc   (X_cc = W_c),   stored transposed in the unused upper triangle.
 // ------------------------------------------------------------------------------------------
 constexpr int L2_LD = 132, L2_WLD = 20, L2_THREADS = 256;
-constexpr int L2_SMEM = (HD_LEAF * L2_LD + 8 * 16 * L2_WLD + 8 * 16 * L2_WLD) * 8;
+constexpr int L2_SMEM = (HD_LEAF * L2_LD + 8 * 16 * L2_WLD + 8 * 16 * L2_WLD + HD_LEAF) * 8;
 
 __device__ __forceinline__ void dmma_tile(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -106,25 +106,45 @@ __device__ __forceinline__ void dmma_tile(double &c0, double &c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
+__device__ long long g_leaf_clk[40];
+#define LEAF_CLK(i) do { if (tid == 0) g_leaf_clk[i] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(L2_THREADS, 1)
 potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
     extern __shared__ __align__(16) double sm[];
     double *As = sm;                          // 128 x 132, column-major: L in the lower triangle, X^T in the upper
     double *Wd = sm + HD_LEAF * L2_LD;        // 8 diagonal-block inverses, W[row][col] at col * 20 + row
     double *Sc = Wd + 8 * 16 * L2_WLD;        // per-warp 16 x 16 scratch, same layout
+    double *Ri = Sc + 8 * 16 * L2_WLD;        // 1 / L_jj
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
-    for (int e = tid; e < HD_LEAF * HD_LEAF; e += L2_THREADS) {
-        const int i = e & 127, j = e >> 7;
-        As[j * L2_LD + i] = (i >= j) ? A[(long) j * lda + i] : 0.0;
+    LEAF_CLK(0);
+    // 16 independent loads in flight per thread (a plain loop is latency-bound: one HBM round trip per element)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double tmp[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = tid + L2_THREADS * (16 * b + u), i = e & 127, j = e >> 7;
+            tmp[u] = (i >= j) ? __ldcs(&A[(long) j * lda + i]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = tid + L2_THREADS * (16 * b + u), i = e & 127, j = e >> 7;
+            As[j * L2_LD + i] = tmp[u];
+        }
     }
     __syncthreads();
+    LEAF_CLK(1);
     for (int p = 0; p < 8; ++p) {
         const int c0 = 16 * p, r0 = c0 + 16, R = HD_LEAF - r0;
         if (warp == 0) {
-            // (a) lane l < 16 owns row l of the diagonal block
-            double a[16], ri[16], w[16];
+            // (a) 16 x 16 diagonal block: lane l (and its mirror l + 16) holds row l in registers; column j is
+            //     broadcast with shuffles.  No branches in the update: entries above the diagonal hold garbage that is
+            //     never read.  1 / L_jj comes from rsqrt (<= 1 ulp) and is kept for the substitutions.
+            const int l = lane & 15;
+            double a[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) a[k] = (lane < 16 && k <= lane) ? As[(c0 + k) * L2_LD + c0 + lane] : 0.0;
+            for (int k = 0; k < 16; ++k) a[k] = As[(c0 + k) * L2_LD + c0 + l];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 double d = __shfl_sync(0xffffffffu, a[j], j);
@@ -132,89 +152,119 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
                     if (lane == 0) atomicCAS(info, 0, base + c0 + j + 1);
                     d = 1.0;
                 }
-                const double r = sqrt(d);
-                ri[j] = 1.0 / r;
-                a[j] = (lane == j) ? r : a[j] * ri[j];
+                const double ri = rsqrt(d);
+                const double r = d * ri;
+                a[j] = (l == j) ? r : a[j] * ri;
+                if (lane == 0) Ri[c0 + j] = ri;
 #pragma unroll
                 for (int k = j + 1; k < 16; ++k) {
-                    const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-                    if (lane >= k) a[k] -= a[j] * lkj;
+                    const double t = __shfl_sync(0xffffffffu, a[j], k);
+                    a[k] = fma(-a[j], t, a[k]);
                 }
-            }
-            // W = L11^-1: lane c owns column c.  w[l] = -(sum_{k=c}^{l-1} L[l][k] w[k]) / L[l][l]
-#pragma unroll
-            for (int l = 0; l < 16; ++l) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < l; ++k) {
-                    const double llk = __shfl_sync(0xffffffffu, a[k], l);
-                    if (k >= lane) s += llk * w[k];
-                }
-                w[l] = (l == lane) ? ri[l] : ((l > lane) ? -s * ri[l] : 0.0);
             }
             if (lane < 16) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k <= lane) As[(c0 + k) * L2_LD + c0 + lane] = a[k];
-                    Wd[p * 16 * L2_WLD + lane * L2_WLD + k] = w[k]; // W[k][lane]
-                }
+                for (int k = 0; k < 16; ++k)
+                    if (k <= l) As[(c0 + k) * L2_LD + c0 + l] = a[k];
             }
         }
         __syncthreads();
+        LEAF_CLK(2 + 3 * p);
         if (R == 0) break;
-        // (b) X = A21 L11^-T by forward substitution, one thread per row (as dtrsm would: no explicit inverse on the
-        //     factor itself, so a single-leaf matrix gets a classical, backward-stable Cholesky)
+        // (b) X = A21 L11^-T by (right-looking) forward substitution, one thread per row -- as dtrsm would: no explicit
+        //     inverse on the factor itself, so a single-leaf matrix gets a classical, backward-stable Cholesky
         if (tid < R) {
             const int m = r0 + tid;
             double x[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                double sacc = As[(c0 + j) * L2_LD + m];
+            for (int j = 0; j < 16; ++j) x[j] = As[(c0 + j) * L2_LD + m];
 #pragma unroll
-                for (int k = 0; k < j; ++k) sacc -= x[k] * As[(c0 + k) * L2_LD + c0 + j];
-                x[j] = sacc / As[(c0 + j) * L2_LD + c0 + j];
+            for (int j = 0; j < 16; ++j) {
+                const double xj = x[j] * Ri[c0 + j];
+                x[j] = xj;
+#pragma unroll
+                for (int k = j + 1; k < 16; ++k) x[k] = fma(-xj, As[(c0 + j) * L2_LD + c0 + k], x[k]);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) As[(c0 + j) * L2_LD + m] = x[j];
         }
         __syncthreads();
-        // (c) A22 -= X X^T on the lower 8x8 tiles
+        LEAF_CLK(3 + 3 * p);
+        // (c) A22 -= X X^T on the lower 8x8 tiles.  Warp w takes tile rows w and T-1-w (T+1 tiles together, balanced),
+        //     four column tiles at a time so that four independent DMMA chains are in flight
         {
             const int T = R / 8;
-            int cnt = 0;
-            for (int mt = 0; mt < T; ++mt)
-                for (int nt = 0; nt <= mt; ++nt) {
-                    if ((cnt++ & 7) != warp) continue;
-                    const int m0 = r0 + 8 * mt, n0 = r0 + 8 * nt;
-                    double c0v = 0, c1v = 0;
+            for (int half = 0; half < 2; ++half) {
+                const int mt = half == 0 ? warp : T - 1 - warp;
+                if (mt < 0 || mt >= T || (half == 1 && mt <= warp) || (half == 0 && 2 * warp > T - 1)) continue;
+                const int m0 = r0 + 8 * mt;
+                double av[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) av[kk] = As[(c0 + 4 * kk + tig) * L2_LD + m0 + gid];
+                for (int nt0 = 0; nt0 <= mt; nt0 += 4) {
+                    double acc[4][2];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const double av = As[(c0 + 4 * kk + tig) * L2_LD + m0 + gid];
-                        const double bv = As[(c0 + 4 * kk + tig) * L2_LD + n0 + gid];
-                        dmma_tile(c0v, c1v, av, bv);
+                        double bv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) bv[q] = As[(c0 + 4 * kk + tig) * L2_LD + r0 + 8 * min(nt0 + q, mt) + gid];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dmma_tile(acc[q][0], acc[q][1], av[kk], bv[q]);
                     }
-                    As[(n0 + 2 * tig) * L2_LD + m0 + gid] -= c0v;
-                    As[(n0 + 2 * tig + 1) * L2_LD + m0 + gid] -= c1v;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (nt0 + q > mt) continue;
+                        const int n0 = r0 + 8 * (nt0 + q);
+                        As[(n0 + 2 * tig) * L2_LD + m0 + gid] -= acc[q][0];
+                        As[(n0 + 2 * tig + 1) * L2_LD + m0 + gid] -= acc[q][1];
+                    }
                 }
+            }
         }
         __syncthreads();
+        LEAF_CLK(4 + 3 * p);
     }
+    LEAF_CLK(26);
     // L back to global (lower only)
     for (int e = tid; e < HD_LEAF * HD_LEAF; e += L2_THREADS) {
         const int i = e & 127, j = e >> 7;
         if (i >= j) A[(long) j * lda + i] = As[j * L2_LD + i];
     }
+    LEAF_CLK(27);
+    // inverses of the 8 diagonal blocks, one per warp: lane c < 16 solves L_rr w = e_c by forward substitution
+    {
+        const int r = warp, rr0 = 16 * r;
+        if (lane < 16) {
+            const double *Bd = As + rr0 * L2_LD + rr0;
+            double w[16];
+#pragma unroll
+            for (int l = 0; l < 16; ++l) w[l] = (l == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const double wk = w[k] * Ri[rr0 + k];
+                w[k] = wk;
+#pragma unroll
+                for (int l = k + 1; l < 16; ++l) w[l] = fma(-wk, Bd[k * L2_LD + l], w[l]);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) Wd[r * 16 * L2_WLD + lane * L2_WLD + k] = (k >= lane) ? w[k] : 0.0; // W[k][lane]
+        }
+    }
+    __syncthreads();
+    LEAF_CLK(28);
     // inverse: warp c builds block column c (blocks r = c+1 .. 7) on its own
     {
         const int c = warp, cc0 = 16 * c;
         double *S = Sc + warp * 16 * L2_WLD;
         for (int r = c + 1; r < 8; ++r) {
             const int rr0 = 16 * r;
-            double acc[2][2][2];
+            double acc[2][2][2], acb[2][2][2]; // two accumulator sets (even / odd k-steps): 8 independent DMMA chains
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = acb[i][j][0] = acb[i][j][1] = 0.0;
             for (int k = c; k < r; ++k) {
                 const int kk0 = 16 * k;
 #pragma unroll
@@ -229,9 +279,16 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) dmma_tile(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                        for (int j = 0; j < 2; ++j) {
+                            if (kk & 1) dmma_tile(acb[i][j][0], acb[i][j][1], av[i], bv[j]);
+                            else dmma_tile(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                        }
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) { acc[i][j][0] += acb[i][j][0]; acc[i][j][1] += acb[i][j][1]; }
             // S (m, n) -> scratch S[n * WLD + m]
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -271,12 +328,14 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
         }
     }
     __syncthreads();
+    LEAF_CLK(29);
     for (int e = tid; e < HD_LEAF * HD_LEAF; e += L2_THREADS) {
         const int i = e & 127, j = e >> 7;
         double v = 0.0;
         if (i >= j) v = ((i >> 4) == (j >> 4)) ? Wd[(i >> 4) * 16 * L2_WLD + (j & 15) * L2_WLD + (i & 15)] : As[i * L2_LD + j];
         Dinv[e] = v;
     }
+    LEAF_CLK(30);
 }
 
 // X leaf (upper triangular) = Dinv^T
@@ -466,10 +525,11 @@ int chol_load_dev(cudaStream_t st, DenseChol *c, const double *dS, long lds) {
 //   side :            wait e_col -> potrf(A_{k+1,k+1}) -> A_{k+2..,k+1} <- A L^-T -> e_panel
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_ev_col = nullptr, g_ev_panel = nullptr;
-static int g_lookahead_nb = 2048; // block size; <= 0 disables the blocked path
+static int g_lookahead_nb = -1; // block size; 0 disables the blocked path; -1 = by size (measured on B200, tools/probe_block.py)
 
 void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
 void hd_chol_set_leaf(int v) { g_leaf_version = v; }
+int hd_leaf_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_leaf_clk, sizeof(long long) * 40) == cudaSuccess ? HD_OK : HD_FAILED; }
 
 static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
     if (!g_side) {
@@ -549,8 +609,10 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
 int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     HD_CALL(ensure_leaf_attr());
     HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
-    if (g_lookahead_nb >= HD_LEAF && c->np >= 4 * g_lookahead_nb)
-        HD_CALL(potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (g_lookahead_nb / HD_LEAF) * HD_LEAF));
+    int nb = g_lookahead_nb;
+    if (nb < 0) nb = c->np < 12000 ? 256 : (c->np < 24000 ? 512 : (c->np < 40000 ? 1024 : 2048));
+    if (nb >= HD_LEAF && c->np >= 4 * nb)
+        HD_CALL(potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF));
     else
         HD_CALL(potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0));
     HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);

@@ -82,6 +82,7 @@ void hd_gemm_set_variant(int v);
 void hd_chol_set_block(int nb);
 void hd_chol_set_leaf(int v);
 void hd_trsv_set_version(int v);
+int hd_leaf_clocks(long long *out);
 
 // ---------------------------------------------------------------------------------------------
 // Dense SPD factorisation object (device resident).

@@ -102,7 +102,7 @@ struct DistRank {
     DenseChol *chol = nullptr;
     bool own_chol = false, own_stream = false;
     cudaStream_t st = nullptr, side = nullptr, push = nullptr;
-    cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_ready = nullptr;
+    cudaEvent_t ev_col = nullptr, ev_diag = nullptr, ev_panel = nullptr, ev_ready = nullptr;
     std::vector<cudaEvent_t> ev_recv; // per panel, recorded on the sender's push stream (same-process delivery)
     char *ctrl = nullptr;
     int *h_ctrl = nullptr;
@@ -167,13 +167,15 @@ int push_panel(DistChol *d, DistRank *R, int k) {
 }
 
 int factor_panel(DistChol *d, DistRank *R, int k) {
-    // side stream: Cholesky of the diagonal block of block column k and the triangular solve of the rows below it
+    // side stream: Cholesky of the diagonal block of block column k (as soon as ev_diag says it is up to date) and the
+    // triangular solve of the rows below it (once ev_col says the rest of the block column is up to date)
     const int nb = d->nb, mp = d->mp;
     const int s = k * nb, b = blk_size(d, k), below = mp - s - b;
     double *L = R->chol->L;
     double *leaves = R->chol->Dinv + (size_t) (s / HD_LEAF) * HD_LEAF * HD_LEAF;
-    HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_col, 0));
+    HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_diag, 0));
     HD_CALL(hd_potrf_rec(R->side, L + (size_t) s * mp + s, mp, b, leaves, R->chol->dinfo, s));
+    HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_col, 0));
     if (below > 0) HD_CALL(hd_trsm_rec(R->side, L + (size_t) s * mp + s + b, mp, below, L + (size_t) s * mp + s, mp, b, leaves));
     HD_CUDA(cudaEventRecord(R->ev_panel, R->side));
     return push_panel(d, R, k);
@@ -200,6 +202,7 @@ int dist_create(DistChol **pd, int n, int nb, int P, int nlocal, const int *rank
         HD_CUDA(cudaStreamCreateWithPriority(&R->side, cudaStreamNonBlocking, hi));
         HD_CUDA(cudaStreamCreateWithPriority(&R->push, cudaStreamNonBlocking, hi));
         HD_CUDA(cudaEventCreateWithFlags(&R->ev_col, cudaEventDisableTiming));
+        HD_CUDA(cudaEventCreateWithFlags(&R->ev_diag, cudaEventDisableTiming));
         HD_CUDA(cudaEventCreateWithFlags(&R->ev_panel, cudaEventDisableTiming));
         HD_CUDA(cudaEventCreateWithFlags(&R->ev_ready, cudaEventDisableTiming));
         R->ev_recv.resize(d->nblk);
@@ -225,7 +228,7 @@ void dist_destroy(DistChol *d) {
         if (R->own_chol) chol_destroy(R->chol);
         if (R->own_stream) cudaStreamDestroy(R->st);
         cudaStreamDestroy(R->side); cudaStreamDestroy(R->push);
-        cudaEventDestroy(R->ev_col); cudaEventDestroy(R->ev_panel); cudaEventDestroy(R->ev_ready);
+        cudaEventDestroy(R->ev_col); cudaEventDestroy(R->ev_diag); cudaEventDestroy(R->ev_panel); cudaEventDestroy(R->ev_ready);
         for (auto &e : R->ev_recv) cudaEventDestroy(e);
         cudaFree(R->ctrl); cudaFreeHost(R->h_ctrl);
         delete R;
@@ -279,6 +282,7 @@ int dist_factor(DistChol *d, int *info_out) {
         HD_CUDA(cudaSetDevice(R->dev));
         HD_CUDA(cudaMemsetAsync(R->chol->dinfo, 0, sizeof(int), R->st));
         HD_CUDA(cudaEventRecord(R->ev_ready, R->st));
+        HD_CUDA(cudaEventRecord(R->ev_diag, R->st));
         HD_CUDA(cudaEventRecord(R->ev_col, R->st));
         for (int q = 0; q < P; ++q) {
             if (q == R->rank || R->peer[q].local) continue;
@@ -318,12 +322,20 @@ int dist_factor(DistChol *d, int *info_out) {
             HD_CUDA(cudaSetDevice(R->dev));
             const int s1 = (k + 1) * nb, b1 = blk_size(d, k + 1);
             const double *Pk = R->chol->L + (size_t) s0 * mp;
+            // diagonal block first: its Cholesky (latency-bound, one CTA at a time) then runs on the side stream while the
+            // main stream updates the rectangle below it
             GemmArgs g{};
-            g.M = mp - s1; g.N = b1; g.K = bk;
+            g.M = b1; g.N = b1; g.K = bk;
             g.A = Pk + s1; g.lda = mp; g.B = Pk + s1; g.ldb = mp; g.C = R->chol->L + (size_t) s1 * mp + s1; g.ldc = mp;
             g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
-            g.bc_nb = b1; g.bc_stride = b1;
             HD_CALL(hd_gemm_nt(R->st, g));
+            HD_CUDA(cudaEventRecord(R->ev_diag, R->st));
+            const int below = mp - s1 - b1;
+            if (below > 0) {
+                g.M = below; g.flags = 0;
+                g.A = Pk + s1 + b1; g.C = R->chol->L + (size_t) s1 * mp + s1 + b1;
+                HD_CALL(hd_gemm_nt(R->st, g));
+            }
             HD_CUDA(cudaEventRecord(R->ev_col, R->st));
             HD_CALL(factor_panel(d, R, k + 1));
         }

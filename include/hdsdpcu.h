@@ -31,9 +31,16 @@ const char *hdsdpcu_version(void);
 long hdsdpcu_launch_count(int reset);
 /* device-to-device copy on the library stream (bench plumbing for HBM-resident inputs) */
 int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes);
-/* tuning knobs for measurements: "gemm_variant" CTA tile / pipeline of the DMMA GEMM: 0 = 128x128x16, 4 stages;
- * 1 = 128x128x32, 3 stages; 2 = 128x64x16, 4 stages, 2 CTAs/SM; 3 = 128x64x32, 2 stages, 2 CTAs/SM (default);
- * "chol_block" NB of the blocked look-ahead Cholesky used when the padded dimension is >= 4 NB (default 2048; 0 = pure recursion) */
+/* debug: clock64() stamps of the phases of the last leaf factorisation (40 values, tools/leafclk.py) */
+int hdsdpcu_debug_leafclk(long long *out);
+/* tuning knobs for measurements (also settable through the environment as HDSDPCU_GEMM_VARIANT / HDSDPCU_CHOL_BLOCK /
+ * HDSDPCU_CHOL_LEAF before hdsdpcu_init):
+ *   "gemm_variant" CTA tile / pipeline of the DMMA GEMM: 0 = 128x128x16, 4 stages; 1 = 128x128x32, 3 stages;
+ *                  2 = 128x64x16, 4 stages, 2 CTAs/SM; 3 = 128x64x32, 2 stages, 2 CTAs/SM (default)
+ *   "chol_block"   NB of the blocked look-ahead Cholesky, used when the padded dimension is >= 4 NB
+ *                  (-1 = chosen by size, the default; 0 = pure recursion)
+ *   "chol_leaf"    128x128 leaf kernel: 1 = column sweep, 2 = DMMA panels (default)
+ *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default) */
 int hdsdpcu_set_option(const char *name, int value);
 
 /* ---------------------------------------------------------------------------------------------
