@@ -199,6 +199,8 @@ def run_ours(args):
             out = [None] * world
             dist.all_gather_object(out, b)
             return out
+        if args.dist_block <= 0:
+            args.dist_block = 512 if world <= 4 else 256   # measured: the panel chain dominates from 8 ranks on
         kkt.dist_init(rank, world, args.dist_block, allgather)
 
     peak = cublas_dgemm_peak(torch) if (rank == 0 and not args.no_peak) else 0.0
@@ -366,7 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=THETA_N)
     ap.add_argument("--edges", type=int, default=THETA_EDGES)
-    ap.add_argument("--dist-block", type=int, default=512, help="block-column width of the multi-GPU distribution of M")
+    ap.add_argument("--dist-block", type=int, default=0, help="block-column width of the multi-GPU distribution of M (0 = 512 up to 4 GPUs, 256 beyond)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peak", action="store_true", help="skip the live cuBLAS DGEMM peak measurement (ncu runs)")
     args = ap.parse_args()
