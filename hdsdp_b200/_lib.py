@@ -94,6 +94,9 @@ _SIGNATURES = {
     "hdsdpcu_kkt_solve_dev": (c_int, [c_void_p, c_int, c_void_p]),
     "hdsdpcu_kkt_setshard": (c_int, [c_void_p, c_int, c_int]),
     "hdsdpcu_debug_leafclk": (c_int, [c_void_p]),
+    "hdsdpcu_linsys_set_indefinite": (c_int, [c_void_p, c_int]),
+    "hdsdpcu_linsys_inertia": (c_int, [c_void_p, c_int_p, c_int_p]),
+    "hdsdpcu_kkt_ldl_status": (c_int, [c_void_p, c_int_p, c_int_p, c_int_p]),
     # multi-GPU Schur matrix
     "hdsdpcu_dist_blob_bytes": (c_int, []),
     "hdsdpcu_dist_owner": (c_int, [c_int, c_int, c_int]),

@@ -145,6 +145,7 @@ static int linsys_solve_host(LinsysCU *l, int nRhs, double *rhs, double *sol, in
         HD_CUDA(cudaMemcpy2DAsync(l->d_vec, (size_t) np * 8, rhs + (size_t) r0 * n, (size_t) n * 8, (size_t) n * 8, nb,
                                   cudaMemcpyHostToDevice, g_stream));
         if (mode == 0 || mode == 2) HD_CALL(chol_fsolve(g_stream, c, l->d_vec, nb, np));
+        if (mode == 2) HD_CALL(chol_dsolve(g_stream, c, l->d_vec, nb, np));
         if (mode == 1 || mode == 2) HD_CALL(chol_bsolve(g_stream, c, l->d_vec, nb, np));
         HD_CUDA(cudaMemcpy2DAsync(out + (size_t) r0 * n, (size_t) n * 8, l->d_vec, (size_t) np * 8, (size_t) n * 8, nb,
                                   cudaMemcpyDeviceToHost, g_stream));
@@ -189,6 +190,17 @@ void hdsdpcu_linsys_destroy(void **pchol) {
     *pchol = nullptr;
 }
 
+int hdsdpcu_linsys_set_indefinite(void *chol, int on) {
+    ((LinsysCU *) chol)->c->ldl = (on != 0);
+    return HD_OK;
+}
+int hdsdpcu_linsys_inertia(void *chol, int *nNegative, int *nPerturbed) {
+    DenseChol *c = ((LinsysCU *) chol)->c;
+    if (!c->ldl || !c->factored) return HD_FAILED;
+    if (nNegative) *nNegative = c->nnegative;
+    if (nPerturbed) *nPerturbed = c->nperturbed;
+    return HD_OK;
+}
 int hdsdpcu_linsys_padded_dim(void *chol) { return ((LinsysCU *) chol)->c->np; }
 int hdsdpcu_linsys_numeric_dev(void *chol, const double *d_elem, long ld, int *info) {
     LinsysCU *l = (LinsysCU *) chol;
@@ -202,6 +214,7 @@ int hdsdpcu_linsys_solve_dev(void *chol, int nRhs, double *d_x, long ldx) {
     LinsysCU *l = (LinsysCU *) chol;
     if (!l->c->factored) return HD_FAILED;
     HD_CALL(chol_fsolve(g_stream, l->c, d_x, nRhs, ldx));
+    HD_CALL(chol_dsolve(g_stream, l->c, d_x, nRhs, ldx));
     return chol_bsolve(g_stream, l->c, d_x, nRhs, ldx);
 }
 int hdsdpcu_linsys_invert_dev(void *chol, double *d_inv) { return chol_invert(g_stream, ((LinsysCU *) chol)->c, d_inv); }
@@ -466,6 +479,13 @@ int hdsdpcu_kkt_export(void *kkt, double *a, double *ard, double *ac, double *cs
     return kkt_export((KktCU *) kkt, a, ard, ac, cscs, cs, csrd, tr);
 }
 int hdsdpcu_kkt_factorize(void *kkt) { return kkt_factorize((KktCU *) kkt, nullptr); }
+int hdsdpcu_kkt_ldl_status(void *kkt, int *isLdl, int *nNegative, int *nPerturbed) {
+    KktCU *k = (KktCU *) kkt;
+    if (isLdl) *isLdl = k->chol->ldl ? 1 : 0;
+    if (nNegative) *nNegative = k->chol->ldl ? k->chol->nnegative : 0;
+    if (nPerturbed) *nPerturbed = k->chol->ldl ? k->chol->nperturbed : 0;
+    return HD_OK;
+}
 int hdsdpcu_kkt_solve(void *kkt, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, 1, rhs, lhs); }
 int hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, nRhs, rhs, lhs); }
 void hdsdpcu_kkt_registerpsdp(void *kkt, int nCones, double **X) {

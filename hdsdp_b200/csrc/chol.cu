@@ -98,7 +98,7 @@ potf2_leaf_kernel(double *A, long lda, double *Dinv, int *info, int base) {
 //   X_rc = -W_r * sum_{k=c}^{r-1} L_rk X_kc   (X_cc = W_c),   stored transposed in the unused upper triangle.
 // ------------------------------------------------------------------------------------------
 constexpr int L2_LD = 132, L2_WLD = 20, L2_THREADS = 256;
-constexpr int L2_SMEM = (HD_LEAF * L2_LD + 8 * 16 * L2_WLD + 8 * 16 * L2_WLD + HD_LEAF) * 8;
+constexpr int L2_SMEM = (HD_LEAF * L2_LD + 8 * 16 * L2_WLD + 8 * 16 * L2_WLD + 2 * HD_LEAF) * 8;
 
 __device__ __forceinline__ void dmma_tile(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -109,13 +109,17 @@ __device__ __forceinline__ void dmma_tile(double &c0, double &c1, double a, doub
 __device__ long long g_leaf_clk[40];
 #define LEAF_CLK(i) do { if (tid == 0) g_leaf_clk[i] = clock64(); } while (0)
 
+// LDL = true: signed Cholesky A = L J L^T with J = diag(+-1) (unpivoted LDL^T with D = J, the scale folded into L);
+// pivots with |d| <= *floorp are replaced by +floorp (static pivoting) and counted.  sgn[j] receives J_jj.
+template <bool LDL>
 __global__ void __launch_bounds__(L2_THREADS, 1)
-potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
+potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base, double *sgn, const double *floorp, int *nperturb) {
     extern __shared__ __align__(16) double sm[];
     double *As = sm;                          // 128 x 132, column-major: L in the lower triangle, X^T in the upper
     double *Wd = sm + HD_LEAF * L2_LD;        // 8 diagonal-block inverses, W[row][col] at col * 20 + row
     double *Sc = Wd + 8 * 16 * L2_WLD;        // per-warp 16 x 16 scratch, same layout
     double *Ri = Sc + 8 * 16 * L2_WLD;        // 1 / L_jj
+    double *Sg = Ri + HD_LEAF;                // J_jj (LDL only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     LEAF_CLK(0);
     // 16 independent loads in flight per thread (a plain loop is latency-bound: one HBM round trip per element)
@@ -148,18 +152,27 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 double d = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(d > 0.0) || isinf(d)) {
+                double sj = 1.0;
+                if (LDL) {
+                    if (d < 0.0) { sj = -1.0; d = -d; }
+                    const double fl = *floorp;
+                    if (!(d > fl) || isinf(d)) { // tiny, zero or NaN pivot: static pivoting
+                        if (lane == 0) atomicAdd(nperturb, 1);
+                        d = fl; sj = 1.0;
+                    }
+                } else if (!(d > 0.0) || isinf(d)) {
                     if (lane == 0) atomicCAS(info, 0, base + c0 + j + 1);
                     d = 1.0;
                 }
                 const double ri = rsqrt(d);
                 const double r = d * ri;
-                a[j] = (l == j) ? r : a[j] * ri;
-                if (lane == 0) Ri[c0 + j] = ri;
+                a[j] = (l == j) ? r : a[j] * (LDL ? ri * sj : ri);
+                if (lane == 0) { Ri[c0 + j] = ri; if (LDL) Sg[c0 + j] = sj; }
+                const double aj = LDL ? sj * a[j] : a[j];
 #pragma unroll
                 for (int k = j + 1; k < 16; ++k) {
                     const double t = __shfl_sync(0xffffffffu, a[j], k);
-                    a[k] = fma(-a[j], t, a[k]);
+                    a[k] = fma(-aj, t, a[k]);
                 }
             }
             if (lane < 16) {
@@ -180,10 +193,11 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
             for (int j = 0; j < 16; ++j) x[j] = As[(c0 + j) * L2_LD + m];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const double xj = x[j] * Ri[c0 + j];
+                const double xj = LDL ? x[j] * Ri[c0 + j] * Sg[c0 + j] : x[j] * Ri[c0 + j];
                 x[j] = xj;
+                const double xs = LDL ? xj * Sg[c0 + j] : xj;
 #pragma unroll
-                for (int k = j + 1; k < 16; ++k) x[k] = fma(-xj, As[(c0 + j) * L2_LD + c0 + k], x[k]);
+                for (int k = j + 1; k < 16; ++k) x[k] = fma(-xs, As[(c0 + j) * L2_LD + c0 + k], x[k]);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) As[(c0 + j) * L2_LD + m] = x[j];
@@ -200,7 +214,7 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
                 const int m0 = r0 + 8 * mt;
                 double av[4];
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) av[kk] = As[(c0 + 4 * kk + tig) * L2_LD + m0 + gid];
+                for (int kk = 0; kk < 4; ++kk) av[kk] = As[(c0 + 4 * kk + tig) * L2_LD + m0 + gid] * (LDL ? Sg[c0 + 4 * kk + tig] : 1.0);
                 for (int nt0 = 0; nt0 <= mt; nt0 += 4) {
                     double acc[4][2];
 #pragma unroll
@@ -227,6 +241,7 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base) {
         LEAF_CLK(4 + 3 * p);
     }
     LEAF_CLK(26);
+    if (LDL && tid < HD_LEAF) sgn[tid] = Sg[tid];
     // L back to global (lower only)
     for (int e = tid; e < HD_LEAF * HD_LEAF; e += L2_THREADS) {
         const int i = e & 127, j = e >> 7;
@@ -379,6 +394,14 @@ __global__ void logdet_kernel(const double *L, long ld, int n, double *out, doub
 
 const int LEAF_SMEM = (HD_LEAF * HD_LEAF + HD_LEAF) * 8;
 
+// LDL^T mode of the recursion (reference fallback dsytrf, linalg/hdsdp_linsolver.c:1662-1825): set by chol_factor around
+// the enqueue; the sign vector of a sub-block is found from its inverse-leaf pointer (leaf index = column / 128)
+struct LdlCtx { double *sgn; const double *dinv_base; const double *floorp; int *nperturb; };
+const LdlCtx *g_ldl = nullptr;
+inline double *sgn_of(const double *dinv) {
+    return g_ldl ? g_ldl->sgn + ((dinv - g_ldl->dinv_base) / (HD_LEAF * HD_LEAF)) * HD_LEAF : nullptr;
+}
+
 int split_leaves(int n) { return ((n / HD_LEAF) / 2) * HD_LEAF; } // n1 (multiple of 128, >= 128 when n >= 256)
 
 // B (rows x n, ld ldb) <- B * L^-T,  L n x n lower (ld ldl), dinv = inverse leaves of L
@@ -389,6 +412,7 @@ int trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, lo
         g.M = rows; g.N = HD_LEAF; g.K = HD_LEAF;
         g.A = B; g.lda = ldb; g.B = dinv; g.ldb = HD_LEAF; g.C = B; g.ldc = ldb;
         g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
+        if (g_ldl) { g.flags = HD_GEMM_EPI_COLSCALE; g.sb = sgn_of(dinv); } // X = (B L^-T) J
         return hd_gemm_nt(st, g); // in place: each CTA reads exactly the rows it later writes
     }
     int n1 = split_leaves(n), n2 = n - n1;
@@ -396,7 +420,7 @@ int trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, lo
     GemmArgs g{};
     g.M = rows; g.N = n2; g.K = n1;
     g.A = B; g.lda = ldb; g.B = L + n1; g.ldb = ldl; g.C = B + (long) n1 * ldb; g.ldc = ldb;
-    g.alpha = -1.0; g.beta = 1.0; g.flags = 0;
+    g.alpha = -1.0; g.beta = 1.0; g.flags = 0; g.ksign = sgn_of(dinv);
     HD_CALL(hd_gemm_nt(st, g));
     return trsm_rec(st, B + (long) n1 * ldb, ldb, rows, L + (long) n1 * ldl + n1, ldl, n2,
                     dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF);
@@ -405,7 +429,8 @@ int trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, lo
 int g_leaf_version = 2;
 int potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base) {
     if (n == HD_LEAF) {
-        if (g_leaf_version == 2) HDK(potf2_leaf2_kernel)<<<1, L2_THREADS, L2_SMEM, st>>>(A, lda, dinv, info, base);
+        if (g_ldl) { ++g_hd_launches; potf2_leaf2_kernel<true><<<1, L2_THREADS, L2_SMEM, st>>>(A, lda, dinv, info, base, sgn_of(dinv), g_ldl->floorp, g_ldl->nperturb); }
+        else if (g_leaf_version == 2) { ++g_hd_launches; potf2_leaf2_kernel<false><<<1, L2_THREADS, L2_SMEM, st>>>(A, lda, dinv, info, base, nullptr, nullptr, nullptr); }
         else HDK(potf2_leaf_kernel)<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, dinv, info, base);
         HD_CUDA(cudaGetLastError());
         return HD_OK;
@@ -416,7 +441,7 @@ int potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *in
     GemmArgs g{};
     g.M = n2; g.N = n2; g.K = n1;
     g.A = A + n1; g.lda = lda; g.B = A + n1; g.ldb = lda; g.C = A + (long) n1 * lda + n1; g.ldc = lda;
-    g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+    g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER; g.ksign = sgn_of(dinv);
     HD_CALL(hd_gemm_nt(st, g));
     return potrf_rec(st, A + (long) n1 * lda + n1, lda, n2, dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF, info,
                      base + n1);
@@ -450,7 +475,8 @@ static int ensure_leaf_attr() {
     cudaGetDevice(&dev);
     if (!(attr >> (dev & 63) & 1ull)) {
         HD_CUDA(cudaFuncSetAttribute(potf2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
-        HD_CUDA(cudaFuncSetAttribute(potf2_leaf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+        HD_CUDA(cudaFuncSetAttribute(potf2_leaf2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+        HD_CUDA(cudaFuncSetAttribute(potf2_leaf2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
         attr |= 1ull << (dev & 63);
     }
     return HD_OK;
@@ -501,6 +527,7 @@ void chol_destroy(DenseChol *c) {
     cudaFree(c->dinfo);
     cudaFreeHost(c->hinfo);
     if (c->work) cudaFree(c->work);
+    if (c->sgn) { cudaFree(c->sgn); cudaFree(c->dfloor); cudaFree(c->dperturb); }
     free(c);
 }
 
@@ -558,7 +585,7 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
         GemmArgs g{};
         g.M = b1; g.N = b1; g.K = b0;
         g.A = P + s1; g.lda = lda; g.B = P + s1; g.ldb = lda; g.C = A + (long) s1 * lda + s1; g.ldc = lda;
-        g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+        g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER; g.ksign = sgn_of(leaves(k));
         HD_CALL(hd_gemm_nt(st, g));
         const int below = np - (s1 + b1);
         if (below > 0) {
@@ -606,23 +633,77 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
     return HD_OK;
 }
 
+namespace {
+__global__ void ldl_floor_kernel(const double *A, long ld, int n, double *floorp, int *nperturb) {
+    __shared__ double red[256];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) v = fmax(v, fabs(A[(long) i * ld + i]));
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *floorp = fmax(1e-13 * red[0], 1e-300); *nperturb = 0; }
+}
+__global__ void sign_scale_kernel(double *x, long ldx, int n, int nrhs, const double *__restrict__ sgn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        for (int r = 0; r < nrhs; ++r) x[(long) r * ldx + i] *= sgn[i];
+}
+__global__ void count_negative_kernel(const double *__restrict__ sgn, int n, int *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && sgn[i] < 0.0) atomicAdd(out, 1);
+}
+} // namespace
+
+// Cholesky (c->ldl == false; *info = LAPACK dpotrf info) or LDL^T with unit-magnitude D (c->ldl == true; always
+// "succeeds": *info = 0, c->nperturbed / c->nnegative report the static pivots and the inertia)
 int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     HD_CALL(ensure_leaf_attr());
     HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
+    LdlCtx ctx{};
+    if (c->ldl) {
+        if (!c->sgn) {
+            HD_CUDA(cudaMalloc(&c->sgn, sizeof(double) * c->np));
+            HD_CUDA(cudaMalloc(&c->dfloor, sizeof(double)));
+            HD_CUDA(cudaMalloc(&c->dperturb, 2 * sizeof(int)));
+        }
+        HDK(ldl_floor_kernel)<<<1, 256, 0, st>>>(c->L, c->np, c->n, c->dfloor, c->dperturb);
+        ctx.sgn = c->sgn; ctx.dinv_base = c->Dinv; ctx.floorp = c->dfloor; ctx.nperturb = c->dperturb;
+        g_ldl = &ctx;
+    }
     int nb = g_lookahead_nb;
     if (nb < 0) nb = c->np < 12000 ? 256 : (c->np < 24000 ? 512 : (c->np < 40000 ? 1024 : 2048));
+    int rc;
     if (nb >= HD_LEAF && c->np >= 4 * nb)
-        HD_CALL(potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF));
+        rc = potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF);
     else
-        HD_CALL(potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0));
+        rc = potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0);
+    g_ldl = nullptr;
+    HD_CALL(rc);
     HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);
     HD_CUDA(cudaGetLastError());
     HD_CUDA(cudaMemcpyAsync(c->hinfo, c->dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int counts[2] = {0, 0};
+    if (c->ldl) {
+        HD_CUDA(cudaMemsetAsync(c->dperturb + 1, 0, sizeof(int), st));
+        HDK(count_negative_kernel)<<<(c->n + 255) / 256, 256, 0, st>>>(c->sgn, c->n, c->dperturb + 1);
+        HD_CUDA(cudaMemcpyAsync(counts, c->dperturb, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     HD_CUDA(cudaStreamSynchronize(st));
     int inf = *c->hinfo;
     if (inf > c->n) inf = 0; // padding pivots are exactly 1
+    if (c->ldl) { inf = 0; c->nperturbed = counts[0]; c->nnegative = counts[1]; }
     if (info) *info = inf;
     c->factored = (inf == 0);
+    return HD_OK;
+}
+
+int chol_dsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx) {
+    if (!c->ldl) return HD_OK;
+    HDK(sign_scale_kernel)<<<(c->n + 255) / 256, 256, 0, st>>>(x, ldx, c->n, nrhs, c->sgn);
+    HD_CUDA(cudaGetLastError());
     return HD_OK;
 }
 

@@ -55,6 +55,7 @@ enum : int {
     HD_GEMM_LOWER = 1,      // only tiles that intersect the lower triangle (m >= n); strict-upper entries untouched
     HD_GEMM_KTRI_MAX = 2,   // operands are "upper triangular in (row,k)": start k at min(m0,n0)... see gemm_nt.cu
     HD_GEMM_EPI_HADSQ = 4,  // epilogue C += sa[m]*sb[n]*acc^2 (rank-one Schur, M2)
+    HD_GEMM_EPI_COLSCALE = 8, // beta == 0 only: C[:, n] = alpha * acc * sb[n]   (LDL^T panel solves: X = (A Dinv^T) J)
 };
 
 struct DenseChol;
@@ -67,6 +68,7 @@ struct GemmArgs {
     int flags;
     const double *sa;   // HADSQ: scale over m
     const double *sb;   // HADSQ: scale over n
+    const double *ksign; // optional +-1 per k: C = alpha * A diag(ksign) B^T + beta C   (LDL^T updates: A22 -= L21 J L21^T)
     // block-cyclic N (distributed Cholesky, dist.cu): the N dimension enumerates only the column blocks this rank owns.
     // Local column c lives at global column (c / bc_nb) * bc_stride + c % bc_nb (relative to B / C); 0 = contiguous.
     int bc_nb, bc_stride;
@@ -98,6 +100,12 @@ struct DenseChol {
     int *hinfo;   // pinned host mirror
     double *work; // np x np workspace (inverse / staging), allocated lazily
     bool factored;
+    // LDL^T fallback (reference dsytrf path): A = L J L^T, J = diag(sgn); allocated on first use
+    bool ldl;
+    double *sgn;     // np entries, +-1
+    double *dfloor;  // device scalar: static-pivoting floor = 1e-13 max|diag A|
+    int *dperturb;   // device: number of pivots replaced by the floor
+    int nperturbed, nnegative;
 };
 
 int chol_create(DenseChol **pc, int n);
@@ -112,6 +120,8 @@ int chol_invert(cudaStream_t st, DenseChol *c, double *inv);
 // in-place triangular solves on nrhs device vectors (each of length >= n, stride ldx)
 int chol_fsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx);
 int chol_bsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx);
+// x <- J x between the two triangular solves of an LDL^T factor (no-op for Cholesky)
+int chol_dsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx);
 // sum_i log(L_ii) * 2 written to *dlogdet (device) ; diag(L) to ddiag (device, n) if non-null
 int hd_trsv(cudaStream_t st, bool transposed, const double *L, long ldl, const double *Dinv, const double *DinvT, int np,
             double *x, int nrhs, long ldx, int *sync);

@@ -72,7 +72,7 @@ __device__ __forceinline__ bool map_tile(const TileMap &tmap, int bid, int &tm, 
 
 // BN = 128: 8 warps (256 threads), one CTA per SM.  BN = 64: 4 warps (128 threads), two CTAs per SM, so one CTA's
 // barrier stalls and C read-modify-write epilogue overlap with the other CTA's main loop.
-template <int BN, int BK, int STAGES, int MINB>
+template <int BN, int BK, int STAGES, int MINB, bool SIGNED>
 __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
     constexpr int NT = BN * 2;
     constexpr int LDB_ = BN + 4;                          // 132 / 68: both = 4 (mod 16) -> conflict-free fragment loads
@@ -161,6 +161,11 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
             double bf[4], af[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) bf[i] = Bs[(kk + tig) * LDB_ + wn + 8 * i + gid];
+            if (SIGNED) {
+                const double sg = __ldg(&g.ksign[k_lo + kt * BK + kk + tig]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bf[i] *= sg;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) af[j] = As[(kk + tig) * LDS_ + wm + 8 * j + gid];
 #pragma unroll
@@ -178,13 +183,16 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
     double *Cw = g.C + (long) (n0 + wn + gid) * g.ldc + m0 + wm + 2 * tig;
     if (interior && !hadsq) {
         if (g.beta == 0.0) {
+            const bool colscale = (g.flags & HD_GEMM_EPI_COLSCALE) != 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
+                const double cs = colscale ? g.alpha * g.sb[n0 + wn + 8 * i + gid] : g.alpha;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+                    double2 v = make_double2(cs * acc[i][j][0], cs * acc[i][j][1]);
                     *reinterpret_cast<double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j) = v;
                 }
+            }
         } else {
             // read-modify-write in batches of 8 independent 16-byte loads (the C tile was prefetched into L2 above)
 #pragma unroll
@@ -239,13 +247,13 @@ int g_variant = 3; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x
 
 template <int BN, int BK, int STAGES> constexpr int smem_bytes() { return STAGES * BK * (LDS_ + BN + 4) * 8; }
 
-template <int BN, int BK, int STAGES, int MINB>
+template <int BN, int BK, int STAGES, int MINB, bool SIGNED = false>
 int launch_variant(cudaStream_t st, const GemmArgs &g) {
     static unsigned long long attr = 0; // one bit per device (function attributes are per context)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(attr >> (dev & 63) & 1ull)) {
-        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smem_bytes<BN, BK, STAGES>()));
         attr |= 1ull << (dev & 63);
     }
@@ -268,7 +276,7 @@ int launch_variant(cudaStream_t st, const GemmArgs &g) {
     }
     long nblocks = nsuper * GROUP * GN;
     ++g_hd_launches;
-    dgemm_nt_kernel<BN, BK, STAGES, MINB><<<(unsigned) nblocks, BN * 2, smem_bytes<BN, BK, STAGES>(), st>>>(g, tmap);
+    dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED><<<(unsigned) nblocks, BN * 2, smem_bytes<BN, BK, STAGES>(), st>>>(g, tmap);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
 }
@@ -299,6 +307,8 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
         if (g.N != BN) return HD_FAILED;
         return launch_variant<128, 32, 3, 1>(st, g);
     }
+    if ((g.flags & HD_GEMM_EPI_COLSCALE) && (g.beta != 0.0 || (g.flags & (HD_GEMM_LOWER | HD_GEMM_EPI_HADSQ)))) return HD_FAILED;
+    if (g.ksign) return launch_variant<64, 32, 2, 2, true>(st, g); // LDL^T fallback path: one instantiation is enough
     switch (g_variant) {
         case 0: return launch_variant<128, 16, 4, 1>(st, g);
         case 1: return launch_variant<128, 32, 3, 1>(st, g);

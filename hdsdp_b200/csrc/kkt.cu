@@ -261,6 +261,15 @@ int kkt_factorize(KktCU *k, int *info_out) {
     HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
     int info = 0;
     HD_CALL(chol_factor(st, k->chol, &info));
+    if (info > 0 && !k->chol->ldl) {
+        // reference HFpLinsysNumeric (linalg/hdsdp_linsolver.c:2030-2039): "KKT system is almost indefinite. Switch to LDL."
+        // -- permanently, as HFpLinsysSwitchToIndefinite does.  Here: unpivoted LDL^T with static pivoting on the GPU.
+        fprintf(stderr, "[hdsdpcu] KKT system is almost indefinite (pivot %d). Switch to LDL.\n", info);
+        k->chol->ldl = true;
+        HD_CUDA(cudaMemcpyAsync(k->chol->L, k->d_M, sizeof(double) * (size_t) k->mp * k->mp, cudaMemcpyDeviceToDevice, st));
+        HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
+        HD_CALL(chol_factor(st, k->chol, &info));
+    }
     if (info_out) *info_out = info;
     k->factored = (info == 0);
     return info == 0 ? HD_OK : HD_FAILED;
@@ -271,6 +280,7 @@ int kkt_solve_dev(KktCU *k, double *d_x, int nRhs) {
     if (!k->factored) return HD_FAILED;
     cudaStream_t st = hd_stream();
     HD_CALL(chol_fsolve(st, k->chol, d_x, nRhs, k->mp));
+    HD_CALL(chol_dsolve(st, k->chol, d_x, nRhs, k->mp));
     HD_CALL(chol_bsolve(st, k->chol, d_x, nRhs, k->mp));
     return HD_OK;
 }

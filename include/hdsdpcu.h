@@ -66,6 +66,12 @@ int  hdsdpcu_linsys_solve(void *chol, int nRhs, double *rhs, double *sol);      
 int  hdsdpcu_linsys_getdiag(void *chol, double *diag);                                /* cholGetDiag */
 void hdsdpcu_linsys_invert(void *chol, double *fullInv, double *aux);                 /* cholInvert  */
 void hdsdpcu_linsys_destroy(void **pchol);                                            /* cholDestroy */
+/* Indefinite back-end (reference lapackIndefiniteLinSolver*, dsytrf/dsytrs, linalg/hdsdp_linsolver.c:1662-1825, selected by
+ * HFpLinsysSwitchToIndefinite :1827 when dpotrf of the Schur matrix fails): with set_indefinite(1) numeric computes the
+ * unpivoted factorisation A = L J L^T, J = diag(+-1), with static pivoting (|pivot| <= 1e-13 max|A_ii| is replaced), solve
+ * applies L^-1, J, L^-T.  Not Bunch-Kaufman: meant for the "almost indefinite" Schur matrices the reference switches on. */
+int  hdsdpcu_linsys_set_indefinite(void *chol, int on);
+int  hdsdpcu_linsys_inertia(void *chol, int *nNegative, int *nPerturbed);
 /* device-resident variants (no host round trip): d_elem has leading dimension ld >= nCol */
 int  hdsdpcu_linsys_padded_dim(void *chol);                   /* leading dimension of the internal buffers */
 int  hdsdpcu_linsys_numeric_dev(void *chol, const double *d_elem, long ld, int *info);
@@ -148,7 +154,8 @@ int  hdsdpcu_kkt_buildupextra_lp(void *kkt, void *lp, const double *colDualInver
 int  hdsdpcu_kkt_regularize(void *kkt, double dKKTReg);
 int  hdsdpcu_kkt_export(void *kkt, double *dASinvVec, double *dASinvRdSinvVec, double *dASinvCSinvVec,
                         double *dCSinvCSinv, double *dCSinv, double *dCSinvRdSinv, double *dTraceSinv);
-int  hdsdpcu_kkt_factorize(void *kkt);
+int  hdsdpcu_kkt_factorize(void *kkt);   /* Cholesky; on a non-positive pivot switches (for good) to the LDL^T back-end */
+int  hdsdpcu_kkt_ldl_status(void *kkt, int *isLdl, int *nNegative, int *nPerturbed);
 int  hdsdpcu_kkt_solve(void *kkt, const double *dRhsVec, double *dLhsVec /* NULL: in place */);
 int  hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *dRhsVec, double *dLhsVec);
 void hdsdpcu_kkt_registerpsdp(void *kkt, int nCones, double **dPrimalX);

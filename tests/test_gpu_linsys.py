@@ -92,3 +92,55 @@ def test_large_factor_residual():
     sign, ld = np.linalg.slogdet(A)
     assert abs(2 * np.log(ls.get_diag()).sum() - ld) <= 1e-10 * abs(ld)
     ls.close()
+
+
+def sym_indefinite(n, seed, nneg):
+    """Symmetric, strongly diagonally dominant by blocks so that unpivoted LDL^T is stable; nneg negative eigen-directions."""
+    rs = np.random.RandomState(seed)
+    d = np.concatenate([-rs.uniform(1.0, 3.0, nneg), rs.uniform(1.0, 3.0, n - nneg)])
+    rs.shuffle(d)
+    E = rs.standard_normal((n, n)) * (0.2 / np.sqrt(n))
+    return np.diag(d) + 0.5 * (E + E.T), d
+
+
+@pytest.mark.parametrize("n,nneg", [(60, 7), (128, 1), (300, 40), (1000, 333), (2500, 5)])
+def test_indefinite_backend_ldl(n, nneg):
+    """Reference a15 (dsytrf/dsytrs fallback, hdsdp_linsolver.c:1662-1825): symmetric indefinite solve + inertia."""
+    import ctypes
+    from hdsdp_b200 import _lib
+    from hdsdp_b200.api import DenseLinsys
+    A, d = sym_indefinite(n, n + nneg, nneg)
+    ls = DenseLinsys(n)
+    lib = _lib.lib()
+    assert lib.hdsdpcu_linsys_set_indefinite(ls.h, 1) == 0
+    assert ls.numeric(np.asfortranarray(A)) == 0
+    neg, pert = ctypes.c_int(-1), ctypes.c_int(-1)
+    assert lib.hdsdpcu_linsys_inertia(ls.h, ctypes.byref(neg), ctypes.byref(pert)) == 0
+    assert neg.value == int((np.linalg.eigvalsh(A) < 0).sum()) and pert.value == 0      # Sylvester: inertia of J
+    rs = np.random.RandomState(0)
+    B = rs.standard_normal((n, 3))
+    X = ls.solve(B)
+    assert np.abs(A @ X - B).max() <= 1e-10 * np.abs(B).max() * n
+    assert np.abs(X - np.linalg.solve(A, B)).max() <= 1e-9 * np.abs(X).max()
+    ls.close()
+
+
+def test_indefinite_backend_static_pivot():
+    """An exactly singular leading pivot is replaced by the floor instead of producing NaN."""
+    import ctypes
+    from hdsdp_b200 import _lib
+    from hdsdp_b200.api import DenseLinsys
+    n = 200
+    A, _ = sym_indefinite(n, 9, 3)
+    A[0, :] = 0.0; A[:, 0] = 0.0
+    ls = DenseLinsys(n)
+    lib = _lib.lib()
+    lib.hdsdpcu_linsys_set_indefinite(ls.h, 1)
+    assert ls.numeric(np.asfortranarray(A)) == 0
+    neg, pert = ctypes.c_int(-1), ctypes.c_int(-1)
+    lib.hdsdpcu_linsys_inertia(ls.h, ctypes.byref(neg), ctypes.byref(pert))
+    assert pert.value == 1
+    b = np.random.RandomState(1).standard_normal(n); b[0] = 0.0
+    x = ls.solve(b)
+    assert np.isfinite(x).all() and np.abs((A @ x - b)[1:]).max() <= 1e-9 * np.abs(b).max()
+    ls.close()

@@ -181,3 +181,35 @@ def test_interior_checks_and_steps():
     S0 = c.get_buffer(api.BUFFER_DUALVAR)
     Sc = c.get_buffer(api.BUFFER_DUALCHECK)
     np.testing.assert_allclose(np.diag(Sc), np.diag(S0) + 5.0, rtol=1e-15)
+
+
+def test_kkt_switches_to_ldl_when_cholesky_fails():
+    """Reference HFpLinsysNumeric (hdsdp_linsolver.c:2030-2039): dpotrf of M fails -> permanent switch to the indefinite
+    back-end, HKKTFactorize still returns OK and HKKTSolve solves the (slightly indefinite) system."""
+    import ctypes
+    from hdsdp_b200 import _lib, api
+    prob, z = load_golden("theta30")
+    sdp, lps, kkt = api.build_problem(prob)
+    p = "pt1_"
+    c = sdp[0]
+    c.set_start(float(z[p + "rd"])); c.update(float(z[p + "tau"]), z[p + "y"])
+    assert c.factorize()
+    kkt.build_up(api.KKT_TYPE_INFEASIBLE)
+    M = np.tril(kkt.get_matrix()); M = M + np.tril(M, -1).T
+    lam = np.linalg.eigvalsh(M)
+    shift = 0.5 * (lam[2] + lam[3])                       # push three eigenvalues below zero
+    assert lam[3] - lam[2] > 1e-6 * lam[-1], "test point must have a spectral gap"
+    kkt.build_up_extra_bound(-shift * np.ones(prob.m), np.zeros(prob.m))
+    assert kkt.factorize() == 0
+    isldl, neg, pert = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    _lib.lib().hdsdpcu_kkt_ldl_status(kkt.h, ctypes.byref(isldl), ctypes.byref(neg), ctypes.byref(pert))
+    assert isldl.value == 1 and neg.value == 3
+    b = np.random.RandomState(3).standard_normal(prob.m)
+    x = kkt.solve(b)
+    Ms = M - shift * np.eye(prob.m)
+    assert np.abs(x - np.linalg.solve(Ms, b)).max() <= 1e-8 * np.abs(x).max()
+    # the switch is permanent (HFpLinsysSwitchToIndefinite): a positive definite M is now solved by LDL as well
+    kkt.build_up(api.KKT_TYPE_INFEASIBLE)
+    assert kkt.factorize() == 0
+    x2 = kkt.solve(b)
+    assert np.abs(x2 - np.linalg.solve(M, b)).max() <= 1e-9 * np.abs(x2).max()
