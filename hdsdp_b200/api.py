@@ -159,6 +159,19 @@ class SDPCone:
         check(self.lib.hdsdpcu_cone_factorize(self.h, int(which), byref(flag)), "HFpLinsysPsdCheck")
         return bool(flag.value)
 
+    def ratio_test(self, dtau: float, dy: np.ndarray, ada_ratio: float, which=BUFFER_DUALVAR) -> float:
+        """HConeRatioTest: largest alpha with S + alpha dS >= 0 (device Lanczos)."""
+        dy = np.ascontiguousarray(dy, dtype=np.float64)
+        step = c_double(0.0)
+        check(self.lib.hdsdpcu_cone_ratiotest(self.h, float(dtau), _dp(dy), float(ada_ratio), int(which), byref(step)), "HConeRatioTest")
+        return step.value
+
+    def lanczos_multiply(self, x: np.ndarray, which=BUFFER_DUALVAR) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        check(self.lib.hdsdpcu_cone_lanczosmultiply(self.h, int(which), _dp(x), _dp(y)), "LanczosMultiply")
+        return y
+
     def get_log_barrier(self, tau: float, y: Optional[np.ndarray], which=BUFFER_DUALVAR) -> float:
         ld = c_double(0.0)
         yy = None if y is None else np.ascontiguousarray(y, dtype=np.float64)

@@ -353,6 +353,13 @@ int hdsdpcu_cone_scal(void *cone, double dScal) {
     return HD_OK;
 }
 
+int hdsdpcu_cone_ratiotest(void *cone, double barHsdTauStep, const double *rowDualStep, double dAdaRatio, int whichBuffer, double *maxStep) {
+    return cone_ratio_test((ConeCU *) cone, barHsdTauStep, rowDualStep, dAdaRatio, whichBuffer, maxStep);
+}
+int hdsdpcu_cone_lanczosmultiply(void *cone, int whichBuffer, const double *x, double *y) {
+    return cone_lanczos_multiply((ConeCU *) cone, whichBuffer, x, y);
+}
+int hdsdpcu_cone_lanczossteps(void *cone) { return cone_lanczos_steps((ConeCU *) cone); }
 int hdsdpcu_cone_buildschur(void *cone, int iCone, void *kkt, int typeKKT) {
     return cone_build_schur((ConeCU *) cone, iCone, (KktCU *) kkt, typeKKT);
 }

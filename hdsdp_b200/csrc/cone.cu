@@ -680,6 +680,7 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
 
 void cone_destroy(ConeCU *c) {
     if (!c) return;
+    lz_destroy(c->lanczos);
     void *ptrs[] = {c->d_pos, c->d_pos_ptr, c->d_ent_con, c->d_ent_val, c->d_dense_packed, c->d_dense_con, c->d_dr1_F,
                     c->d_dr1_W, c->d_dr1_con, c->d_dr1_sign, c->d_coef, c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_sinv,
                     c->d_scal, c->d_r_con, c->d_r_sign, c->d_r_At, c->d_r_Vt, c->d_r_unit, c->d_r_sp_ptr, c->d_r_sp_idx,

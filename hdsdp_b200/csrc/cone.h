@@ -29,6 +29,7 @@ struct SsGroup { int first, count, ent_first, ent_count; };
 
 struct KktCU;
 struct DistChol;
+struct LanczosCU;
 
 struct ConeCU {
     int m = 0;   // constraints
@@ -94,6 +95,7 @@ struct ConeCU {
 
     double *d_U = nullptr, *d_B = nullptr; // np x np workspaces for explicit S^-1 A S^-1
     bool sinv_valid = false;
+    LanczosCU *lanczos = nullptr; // ratio-test state (lanczos.cu), created on first use
 };
 
 struct KktCU {
@@ -134,6 +136,11 @@ int cone_update_buffer(ConeCU *c, double cCoef, double aScal, const double *aCoe
                        double eyeCoef, int which);
 int cone_factorize(ConeCU *c, int which, int *isPsd);
 int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT);
+// lanczos.cu
+int cone_ratio_test(ConeCU *c, double dTauStep, const double *dyHost, double dAdaRatio, int which, double *maxStep);
+int cone_lanczos_multiply(ConeCU *c, int which, const double *x, double *y);
+int cone_lanczos_steps(ConeCU *c);
+void lz_destroy(LanczosCU *l);
 
 int kkt_create(KktCU **pk, int nRow);
 void kkt_destroy(KktCU *k);

@@ -117,6 +117,16 @@ int  hdsdpcu_cone_getbarrier(void *cone, double barHsdTau, const double *rowDual
                              double *logdet);
 int  hdsdpcu_cone_addstepandcheck(void *cone, double dStep, int whichBuffer, int *isInterior);
 int  hdsdpcu_cone_buildschur(void *cone, int iCone, void *kkt, int typeKKT);
+/* Dual ratio test on the device.  ratiotest = coneRatioTest (sdpDenseConeRatioTestImpl, hdsdp_conic_sdp.c:1642):
+ * dS = dAdaRatio Rd I - A' dy + dTau C into BUFFER_DUALSTEP, then the reference's Lanczos (linalg/hdsdp_lanczos.c:161: same
+ * srand(n) start vector, check frequency, residual tests and step formula) on w -> -L^-1 dS L^-T w with every n-vector in HBM;
+ * *maxStep = largest alpha with S + alpha dS >= 0 (INFINITY if none).  whichBuffer selects the factor (DUALVAR / DUALCHECK),
+ * which must be current (hdsdpcu_cone_factorize / _getbarrier).  lanczosmultiply = one operator application with host
+ * vectors (sdpDenseConeILanczosMultiply :462) for a host-side HLanczosSolve; lanczossteps = steps of the last ratio test. */
+int  hdsdpcu_cone_ratiotest(void *cone, double barHsdTauStep, const double *rowDualStep, double dAdaRatio, int whichBuffer,
+                            double *maxStep);
+int  hdsdpcu_cone_lanczosmultiply(void *cone, int whichBuffer, const double *x, double *y);
+int  hdsdpcu_cone_lanczossteps(void *cone);
 /* Hand the cone an S^-1 computed elsewhere (used by the integration shim, whose S factor is owned by the
  * reference's hdsdp_linsys_fp): from a host n x n matrix, or device-to-device from a hdsdpcu_linsys handle
  * (HFpLinsysInvert, linalg/hdsdp_linsolver.c:2120, without the host round trip).  Valid until the next update. */

@@ -111,6 +111,13 @@ int refdrv_set_point(refdrv *h, const double *y, double tau, double rd, double *
     return 0;
 }
 
+/* HConeRatioTest (interface/hdsdp_conic.c:270 -> sdpDenseConeRatioTestImpl hdsdp_conic_sdp.c:1642): largest step alpha with
+ * S + alpha dS >= 0 for cone k, dS = dAdaRatio*Rd*I - A'dy + dTau*C, by the reference's Lanczos (linalg/hdsdp_lanczos.c:161).
+ * Requires refdrv_set_point before (S factorised). */
+int refdrv_ratio_test(refdrv *h, int k, double dTau, const double *dy, double dAdaRatio, int whichBuffer, double *maxStep) {
+    return (int) HConeRatioTest(h->cones[k], dTau, (double *) dy, dAdaRatio, whichBuffer, maxStep);
+}
+
 int refdrv_interior_check(refdrv *h, const double *y, double tau, int *isInterior) {
     int all = 1;
     for (int k = 0; k < h->nCones; ++k) {

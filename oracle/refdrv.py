@@ -39,6 +39,8 @@ def lib():
         l.refdrv_is_kkt_sparse.argtypes = [c_void_p]
         l.refdrv_set_point.argtypes = [c_void_p, c_double_p, c_double, c_double, c_double_p]
         l.refdrv_interior_check.argtypes = [c_void_p, c_double_p, c_double, c_int_p]
+        if hasattr(l, "refdrv_ratio_test"):
+            l.refdrv_ratio_test.argtypes = [c_void_p, c_int, c_double, c_double_p, c_double, c_int, c_double_p]
         l.refdrv_build.argtypes = [c_void_p, c_int, c_int]
         l.refdrv_regularize.argtypes = [c_void_p, c_double]
         l.refdrv_get_M.argtypes = [c_void_p, c_double_p]
@@ -112,6 +114,15 @@ class RefKKT:
         f = c_int(0)
         self.l.refdrv_interior_check(self.h, _dp(y), float(tau), byref(f))
         return bool(f.value)
+
+    def ratio_test(self, k, dtau, dy, ada_ratio, which=0) -> float:
+        """HConeRatioTest on cone k (reference Lanczos); set_point must have been called."""
+        dy = np.ascontiguousarray(dy, dtype=np.float64)
+        step = c_double(0.0)
+        rc = self.l.refdrv_ratio_test(self.h, int(k), float(dtau), _dp(dy), float(ada_ratio), int(which), byref(step))
+        if rc != 0:
+            raise RuntimeError(f"reference HConeRatioTest failed rc={rc}")
+        return step.value
 
     def build(self, type_kkt=0, strategy=-1):
         rc = self.l.refdrv_build(self.h, int(type_kkt), int(strategy))
