@@ -29,6 +29,7 @@ void classify_coeff(int n, int nnz, const int *Ci, const double *Cx, HostCoeff &
 namespace {
 
 constexpr int SS_MAX_NNZ = 16;
+constexpr int DD_MIN = 16;          // dense rows from which the dense x dense block is built as one Gram GEMM
 constexpr int SS_SMEM_BUDGET = 192 * 1024;
 
 template <typename T> int upload(T **dptr, const std::vector<T> &h) {
@@ -461,6 +462,53 @@ __global__ void dense_dot_kernel(const double *__restrict__ D, long dstride, con
     }
 }
 
+// ---- batched dense x dense block -----------------------------------------------------------------------------------
+// out[i + q * ndp] = in[q + i * np2]   (np2 x nd  ->  ndp x np2, constraint index fastest; rows nd..ndp-1 stay zero)
+__global__ void dd_to_vec_kernel(const double *__restrict__ in, long np2, int nd, double *out, int ndp) {
+    __shared__ double t[32][33];
+    const long q0 = (long) blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = i0 + r; const long q = q0 + threadIdx.x;
+        t[r][threadIdx.x] = (i < nd && q < np2) ? in[q + (long) i * np2] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const long q = q0 + r; const int i = i0 + threadIdx.x;
+        if (q < np2 && i < ndp) out[i + q * ndp] = t[threadIdx.x][r];
+    }
+}
+// Ut[i + (c + r*np) * ndp] = U[i + (r + c*np) * ndp]
+__global__ void dd_swap_kernel(const double *__restrict__ U, double *Ut, int np, int ndp) {
+    const int c = blockIdx.y, r = blockIdx.z;
+    const double *src = U + ((long) r + (long) c * np) * ndp;
+    double *dst = Ut + ((long) c + (long) r * np) * ndp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ndp; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+// M[max(ci,cj), min] += G[i, j] (i >= j)
+__global__ void dd_scatter_kernel(const double *__restrict__ G, long ldg, int nd, const int *__restrict__ con, double *M, long ldm, Shard sh) {
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    if (i >= nd) return;
+    const int ci = con[i];
+    for (int jj = threadIdx.y; jj < 32; jj += 8) {
+        const int j = blockIdx.y * 32 + jj;
+        if (j > i || j >= nd) continue;
+        const int cj = con[j];
+        const int r = max(ci, cj), cc = min(ci, cj);
+        if (owns_col(sh, cc)) M[(long) cc * ldm + r] += G[(long) j * ldg + i];
+    }
+}
+// vec[con_i] += scale * sum_{c,r} U_i[c, r] * X[r, c]   (tr(U_i X)); one thread per constraint, coalesced over i
+__global__ void dd_trace_kernel(const double *__restrict__ U, int ndp, int nd, int np, int n, const double *__restrict__ X, long ldx,
+                                const int *__restrict__ con, double scale, double *vec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    double s = 0.0;
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) s += U[i + ((long) c + (long) r * np) * ndp] * X[(long) c * ldx + r];
+    vec[con[i]] += scale * s;
+}
+
 __global__ void vec_add_scalar_kernel(double *vec, int i, const double *src, double scale) { vec[i] += scale * (*src); }
 
 bool g_ss_attr = false;
@@ -649,6 +697,16 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
             HD_CUDA(cudaMemcpy(c->d_dn_full + (size_t) d * np * np, full.data(), sizeof(double) * full.size(), cudaMemcpyHostToDevice));
         }
         HD_CALL(upload(&c->d_dn_con, d_con));
+        if (c->nd >= DD_MIN) {
+            c->ndp = hd_pad(c->nd);
+            const size_t bytes = sizeof(double) * (size_t) c->ndp * np * np;
+            HD_CUDA(cudaMalloc(&c->d_dn_vec, bytes)); HD_CUDA(cudaMalloc(&c->d_dn_U, bytes)); HD_CUDA(cudaMalloc(&c->d_dn_Ut, bytes));
+            HD_CUDA(cudaMalloc(&c->d_dn_G, sizeof(double) * (size_t) c->ndp * c->ndp));
+            HD_CUDA(cudaMemset(c->d_dn_vec, 0, bytes));
+            const long np2 = (long) np * np;
+            dd_to_vec_kernel<<<dim3((unsigned) ((np2 + 31) / 32), (unsigned) ((c->ndp + 31) / 32)), dim3(32, 8)>>>(c->d_dn_full, np2, c->nd, c->d_dn_vec, c->ndp);
+            HD_CUDA(cudaDeviceSynchronize());
+        }
     }
     // objective
     {
@@ -681,6 +739,7 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
 void cone_destroy(ConeCU *c) {
     if (!c) return;
     lz_destroy(c->lanczos);
+    cudaFree(c->d_dn_vec); cudaFree(c->d_dn_U); cudaFree(c->d_dn_Ut); cudaFree(c->d_dn_G);
     void *ptrs[] = {c->d_pos, c->d_pos_ptr, c->d_ent_con, c->d_ent_val, c->d_dense_packed, c->d_dense_con, c->d_dr1_F,
                     c->d_dr1_W, c->d_dr1_con, c->d_dr1_sign, c->d_coef, c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_sinv,
                     c->d_scal, c->d_r_con, c->d_r_sign, c->d_r_At, c->d_r_Vt, c->d_r_unit, c->d_r_sp_ptr, c->d_r_sp_idx,
@@ -788,6 +847,15 @@ static int explicit_B_full(ConeCU *c, cudaStream_t st, const double *Afull) {
     return hd_gemm_nt(st, g);
 }
 
+// U_i = A_i Sinv for ALL dense rows in one GEMM: rows (i, c) of the vec layout are an affine index, K = k
+static int dd_compute_U(ConeCU *c, cudaStream_t st) {
+    GemmArgs g{};
+    g.M = c->ndp * c->np; g.N = c->np; g.K = c->np;
+    g.A = c->d_dn_vec; g.lda = (long) c->ndp * c->np; g.B = c->d_sinv; g.ldb = c->np; g.C = c->d_dn_U; g.ldc = (long) c->ndp * c->np;
+    g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
+    return hd_gemm_nt(st, g);
+}
+
 int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
     cudaStream_t st = hd_stream();
     const int n = c->n, np = c->np;
@@ -845,7 +913,14 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
                                                                 k->d_asinv, k->d_asinvrd);
     }
     // dense rows: asinvrd needs tr(B_i); done together with the matrix below (also for correctors)
-    if (c->nd > 0 && rd != 0.0 && !build_matrix && do_vectors) {
+    const bool dd_batched = c->d_dn_vec != nullptr;
+    const bool dd_only = dd_batched && c->nss == 0 && c->nsb == 0 && c->nr == 0; // no other class needs the explicit B_i
+    if (dd_batched && (build_matrix || (rd != 0.0 && do_vectors))) {
+        HD_CALL(dd_compute_U(c, st));
+        if (rd != 0.0 && do_vectors) // tr(Sinv A_i Sinv) = tr(U_i Sinv)
+            HDK(dd_trace_kernel)<<<nblk(c->nd, 128), 128, 0, st>>>(c->d_dn_U, c->ndp, c->nd, np, n, Sinv, np, c->d_dn_con, rd, k->d_asinvrd);
+    }
+    if (c->nd > 0 && rd != 0.0 && !build_matrix && do_vectors && !dd_batched) {
         for (int d = 0; d < c->nd; ++d) {
             HD_CALL(explicit_B_full(c, st, c->d_dn_full + (size_t) d * np * np));
             HD_CUDA(cudaMemsetAsync(c->d_scal, 0, sizeof(double), st));
@@ -917,9 +992,22 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
                                                      c->d_r_sign, c->nr, c->d_r_Vt, 1, c->nrp, nullptr, k->d_M, ldm, sh);
         HD_CUDA(cudaGetLastError());
     }
+    // D x D as one Gram GEMM: M_ij = tr(A_i Sinv A_j Sinv) = <vec(U_i), vec(U_j^T)>, K = np^2
+    if (dd_batched) {
+        HDK(dd_swap_kernel)<<<dim3(nblk(c->ndp, 256), np, np), 256, 0, st>>>(c->d_dn_U, c->d_dn_Ut, np, c->ndp);
+        GemmArgs g{};
+        g.M = c->ndp; g.N = c->ndp; g.K = np * np;
+        g.A = c->d_dn_U; g.lda = c->ndp; g.B = c->d_dn_Ut; g.ldb = c->ndp; g.C = c->d_dn_G; g.ldc = c->ndp;
+        g.alpha = 1.0; g.beta = 0.0; g.flags = HD_GEMM_LOWER;
+        HD_CALL(hd_gemm_nt(st, g));
+        int t = (c->nd + 31) / 32;
+        HDK(dd_scatter_kernel)<<<dim3(t, t), dim3(32, 8), 0, st>>>(c->d_dn_G, c->ndp, c->nd, c->d_dn_con, k->d_M, ldm, sh);
+        HD_CUDA(cudaGetLastError());
+    }
     // explicit rows: SB (big sparse) then D (dense); B_i = Sinv A_i Sinv, then <A_j, B_i> for every other class
     for (int pass = 0; pass < 2; ++pass) {
         const int cnt = (pass == 0) ? c->nsb : c->nd;
+        if (pass == 1 && dd_only) break; // dense rows only meet dense rows: everything came from the Gram GEMM
         for (int b = 0; b < cnt; ++b) {
             int ci;
             if (pass == 0) {
@@ -928,7 +1016,7 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
             } else {
                 ci = c->d_con_host[b];
                 HD_CALL(explicit_B_full(c, st, c->d_dn_full + (size_t) b * np * np));
-                if (rd != 0.0 && do_vectors) {
+                if (rd != 0.0 && do_vectors && !dd_batched) {
                     HD_CUDA(cudaMemsetAsync(c->d_scal, 0, sizeof(double), st));
                     HDK(trace_kernel)<<<1, 256, 0, st>>>(c->d_B, np, n, rd, c->d_scal);
                     HDK(vec_add_scalar_kernel)<<<1, 1, 0, st>>>(k->d_asinvrd, ci, c->d_scal, 1.0);
@@ -946,7 +1034,7 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
                                                                      c->nsb, (pass == 0) ? b : 0, 1, 1.0, nullptr, k->d_M, ldm, ci, sh);
             if (c->nd > 0) {
                 int dmin = (pass == 0) ? c->nd : b; // SB x D pairs are produced in the D pass (row = dense)
-                if (dmin < c->nd)
+                if (dmin < c->nd && !(pass == 1 && dd_batched))
                     HDK(dense_dot_kernel)<<<c->nd - dmin, 256, 0, st>>>(c->d_dn_full, (long) np * np, B, np, n, c->d_dn_con, dmin, 1, 1.0, nullptr,
                                                                    k->d_M, ldm, ci, sh);
             }

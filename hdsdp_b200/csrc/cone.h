@@ -87,6 +87,10 @@ struct ConeCU {
     int nd = 0;
     std::vector<int> d_con_host;
     double *d_dn_full = nullptr; // [np*np x nd] each matrix full symmetric np x np (zero padded)
+    // batched dense x dense block (nd >= DD_MIN): "vec" layout, constraint index fastest:
+    //   d_dn_vec[i + (c + k*np) * ndp] = A_i[c, k];  U / Ut workspaces of the same shape, G ndp x ndp
+    int ndp = 0;
+    double *d_dn_vec = nullptr, *d_dn_U = nullptr, *d_dn_Ut = nullptr, *d_dn_G = nullptr;
     int *d_dn_con = nullptr;
     // objective in Schur-usable form
     int obj_type = COEFF_ZERO;
