@@ -166,6 +166,14 @@ class SDPCone:
         check(self.lib.hdsdpcu_cone_ratiotest(self.h, float(dtau), _dp(dy), float(ada_ratio), int(which), byref(step)), "HConeRatioTest")
         return step.value
 
+    def get_primal(self, mu: float, y: np.ndarray, dy: np.ndarray):
+        """HConeGetPrimal: X = mu (S^-1 + S^-1 dS S^-1) with S = C - A'y, dS = A'dy; None if S is not positive definite."""
+        y = np.ascontiguousarray(y, dtype=np.float64); dy = np.ascontiguousarray(dy, dtype=np.float64)
+        X = np.zeros((self.n, self.n), order="F")
+        ok = c_int(0)
+        check(self.lib.hdsdpcu_cone_getprimal(self.h, float(mu), _dp(y), _dp(dy), _dp(X), byref(ok)), "HConeGetPrimal")
+        return X if ok.value else None
+
     def lanczos_multiply(self, x: np.ndarray, which=BUFFER_DUALVAR) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.zeros_like(x)

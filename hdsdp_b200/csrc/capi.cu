@@ -353,6 +353,9 @@ int hdsdpcu_cone_scal(void *cone, double dScal) {
     return HD_OK;
 }
 
+int hdsdpcu_cone_getprimal(void *cone, double dBarrierMu, const double *dRowDual, const double *dRowDualStep, double *dConePrimal, int *isFeasible) {
+    return cone_get_primal((ConeCU *) cone, dBarrierMu, dRowDual, dRowDualStep, dConePrimal, isFeasible);
+}
 int hdsdpcu_cone_ratiotest(void *cone, double barHsdTauStep, const double *rowDualStep, double dAdaRatio, int whichBuffer, double *maxStep) {
     return cone_ratio_test((ConeCU *) cone, barHsdTauStep, rowDualStep, dAdaRatio, whichBuffer, maxStep);
 }

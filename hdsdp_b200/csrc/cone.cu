@@ -739,6 +739,7 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
 void cone_destroy(ConeCU *c) {
     if (!c) return;
     lz_destroy(c->lanczos);
+    cudaFree(c->d_prim);
     cudaFree(c->d_dn_vec); cudaFree(c->d_dn_U); cudaFree(c->d_dn_Ut); cudaFree(c->d_dn_G);
     void *ptrs[] = {c->d_pos, c->d_pos_ptr, c->d_ent_con, c->d_ent_val, c->d_dense_packed, c->d_dense_con, c->d_dr1_F,
                     c->d_dr1_W, c->d_dr1_con, c->d_dr1_sign, c->d_coef, c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_sinv,
@@ -845,6 +846,48 @@ static int explicit_B_full(ConeCU *c, cudaStream_t st, const double *Afull) {
     HD_CALL(hd_gemm_nt(st, g));
     g.B = c->d_U; g.C = c->d_B; // B = Sinv * U^T = Sinv A Sinv
     return hd_gemm_nt(st, g);
+}
+
+// Primal recovery (reference sdpDenseConeGetPrimal, hdsdp_conic_sdp.c:2395-2446):
+//   S = C - A'y (BUFFER_DUALCHECK, must be positive definite), dS = A'dy,  X = mu (S^-1 + S^-1 dS S^-1), symmetrised.
+// The reference applies four n-rhs triangular solves; here S^-1 comes from the GEMM-based inverse and the two
+// products are DMMA GEMMs.  *isFeasible = 0 ("Recovery step is infeasible"): X is not written.
+__global__ void primal_combine_kernel(const double *__restrict__ Sinv, const double *__restrict__ B, double *X, long ld, int n, double mu) {
+    const int i = blockIdx.x * 32 + threadIdx.x, j0 = blockIdx.y * 32;
+    if (i >= n) return;
+    for (int jj = threadIdx.y; jj < 32; jj += 8) {
+        const int j = j0 + jj;
+        if (j >= n) continue;
+        const double v = Sinv[(long) j * ld + i] + 0.5 * (B[(long) j * ld + i] + B[(long) i * ld + j]);
+        X[(long) j * ld + i] = mu * v;
+    }
+}
+
+int cone_get_primal(ConeCU *c, double mu, const double *yHost, const double *dyHost, double *Xhost, int *isFeasible) {
+    cudaStream_t st = hd_stream();
+    const int n = c->n, np = c->np;
+    int psd = 0;
+    HD_CALL(cone_update_buffer(c, 1.0, -1.0, yHost, nullptr, 0.0, BUF_DUALCHECK));       // sdpDenseConeInteriorCheckExpert(1, -1, y, 0)
+    HD_CALL(cone_factorize(c, BUF_DUALCHECK, &psd));
+    if (isFeasible) *isFeasible = psd;
+    if (!psd) return HD_OK;
+    HD_CALL(cone_update_buffer(c, 0.0, 1.0, dyHost, nullptr, 0.0, BUF_DUALSTEP));        // dS = A' dy
+    HD_CALL(hd_symmetrize_lower(st, c->d_buf[BUF_DUALSTEP], np, np));
+    HD_CALL(ensure_UB(c));
+    if (!c->d_prim) HD_CUDA(cudaMalloc(&c->d_prim, sizeof(double) * (size_t) np * np));
+    HD_CALL(chol_invert(st, c->checker, c->d_prim));                                       // S^-1 (full symmetric)
+    GemmArgs g{};
+    g.M = np; g.N = np; g.K = np; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
+    g.A = c->d_prim; g.lda = np; g.B = c->d_buf[BUF_DUALSTEP]; g.ldb = np; g.C = c->d_U; g.ldc = np;   // U = S^-1 dS
+    HD_CALL(hd_gemm_nt(st, g));
+    g.A = c->d_U; g.B = c->d_prim; g.C = c->d_B;                                                        // B = U S^-1
+    HD_CALL(hd_gemm_nt(st, g));
+    int t = (n + 31) / 32;
+    HDK(primal_combine_kernel)<<<dim3(t, t), dim3(32, 8), 0, st>>>(c->d_prim, c->d_B, c->d_U, np, n, mu);
+    HD_CUDA(cudaGetLastError());
+    HD_CUDA(cudaMemcpy2DAsync(Xhost, (size_t) n * 8, c->d_U, (size_t) np * 8, (size_t) n * 8, n, cudaMemcpyDeviceToHost, st));
+    HD_CUDA(cudaStreamSynchronize(st));
+    return HD_OK;
 }
 
 // U_i = A_i Sinv for ALL dense rows in one GEMM: rows (i, c) of the vec layout are an affine index, K = k

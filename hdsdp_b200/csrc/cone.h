@@ -98,6 +98,7 @@ struct ConeCU {
     double *d_obj_full = nullptr; // dense / rank-one C expanded to full np x np
 
     double *d_U = nullptr, *d_B = nullptr; // np x np workspaces for explicit S^-1 A S^-1
+    double *d_prim = nullptr;              // np x np: S^-1 of the checker buffer (primal recovery)
     bool sinv_valid = false;
     LanczosCU *lanczos = nullptr; // ratio-test state (lanczos.cu), created on first use
 };
@@ -140,6 +141,7 @@ int cone_update_buffer(ConeCU *c, double cCoef, double aScal, const double *aCoe
                        double eyeCoef, int which);
 int cone_factorize(ConeCU *c, int which, int *isPsd);
 int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT);
+int cone_get_primal(ConeCU *c, double mu, const double *yHost, const double *dyHost, double *Xhost, int *isFeasible);
 // lanczos.cu
 int cone_ratio_test(ConeCU *c, double dTauStep, const double *dyHost, double dAdaRatio, int which, double *maxStep);
 int cone_lanczos_multiply(ConeCU *c, int which, const double *x, double *y);

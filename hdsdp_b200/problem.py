@@ -15,6 +15,7 @@ The generators are the deterministic synthetic inputs named in SURVEY.md section
 """
 from __future__ import annotations
 
+import os
 import random
 import re
 from dataclasses import dataclass, field
@@ -300,3 +301,51 @@ def gen_random_sparse(n: int, m: int, nnz_per_row: int = 3, seed: int = 7, dense
                 cols.append(0); rows.append(int(pack_idx(n, r, c))); vals.append(-Cm[r, c])
     beg, idx, elem = _csc_from_triplets(m + 1, cols, rows, vals)
     return Problem(m=m, cones=[ConeData("sdp", n, beg, idx, elem)], rhs=b, name=f"randsparse_n{n}_m{m}_s{seed}")
+
+
+# --------------------------------------------------------------------------------------------------
+# Binary container.  The reference reads SDPA text (HReadSDPA, interface/hdsdp_file_io.c:34) into the
+# user_data CSC arrays (def_hdsdp_user_data.h:11-32); config D is ~1.2 M text lines and config E 1.2 GB of CSC, so the
+# graded synthetic inputs travel as the CSC arrays themselves: one little-endian file, memory-mappable, no parsing.
+#   header  : magic "HDSDPB1\0", int64 m, int64 ncones
+#   per cone: int64 kind (0 sdp, 1 lp), int64 dim, int64 nnz, then beg int32[m+2], idx int32[nnz], elem float64[nnz]
+#             (each array padded to 8 bytes)
+#   trailer : rhs float64[m]
+# --------------------------------------------------------------------------------------------------
+_MAGIC = b"HDSDPB1\0"
+
+
+def save_bin(prob: Problem, path: str) -> None:
+    def pad8(f, nbytes):
+        f.write(b"\0" * ((-nbytes) % 8))
+    with open(path, "wb") as f:
+        f.write(_MAGIC)
+        np.array([prob.m, len(prob.cones)], dtype="<i8").tofile(f)
+        for c in prob.cones:
+            np.array([0 if c.kind == "sdp" else 1, c.dim, len(c.elem)], dtype="<i8").tofile(f)
+            beg = np.ascontiguousarray(c.beg, dtype="<i4"); idx = np.ascontiguousarray(c.idx, dtype="<i4")
+            assert len(beg) == prob.m + 2 and len(idx) == len(c.elem)
+            beg.tofile(f); pad8(f, beg.nbytes)
+            idx.tofile(f); pad8(f, idx.nbytes)
+            np.ascontiguousarray(c.elem, dtype="<f8").tofile(f)
+        np.ascontiguousarray(prob.rhs, dtype="<f8").tofile(f)
+
+
+def load_bin(path: str, mmap: bool = True) -> Problem:
+    """Zero-copy when mmap=True: the CSC arrays are views of the file, handed straight to hdsdpcu_cone_create."""
+    raw = np.memmap(path, dtype=np.uint8, mode="r") if mmap else np.fromfile(path, dtype=np.uint8)
+    if bytes(raw[:8]) != _MAGIC:
+        raise ValueError(f"{path}: not an HDSDPB1 file")
+    off = 8
+    m, ncones = (int(v) for v in raw[off:off + 16].view("<i8")); off += 16
+    cones = []
+    for _ in range(ncones):
+        kind, dim, nnz = (int(v) for v in raw[off:off + 24].view("<i8")); off += 24
+        nb = 4 * (m + 2)
+        beg = raw[off:off + nb].view("<i4"); off += nb + ((-nb) % 8)
+        nb = 4 * nnz
+        idx = raw[off:off + nb].view("<i4"); off += nb + ((-nb) % 8)
+        elem = raw[off:off + 8 * nnz].view("<f8"); off += 8 * nnz
+        cones.append(ConeData("sdp" if kind == 0 else "lp", dim, beg, idx, elem))
+    rhs = raw[off:off + 8 * m].view("<f8")
+    return Problem(m=m, cones=cones, rhs=rhs, name=os.path.basename(path))

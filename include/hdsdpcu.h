@@ -127,6 +127,11 @@ int  hdsdpcu_cone_ratiotest(void *cone, double barHsdTauStep, const double *rowD
                             double *maxStep);
 int  hdsdpcu_cone_lanczosmultiply(void *cone, int whichBuffer, const double *x, double *y);
 int  hdsdpcu_cone_lanczossteps(void *cone);
+/* Primal recovery.  conePRecover = sdpDenseConeGetPrimal (hdsdp_conic_sdp.c:2395-2446): with S = C - A'y
+ * (checked for positive definiteness in BUFFER_DUALCHECK) and dS = A'dy, dConePrimal (n x n, column-major, full symmetric)
+ * = mu (S^-1 + S^-1 dS S^-1).  *isFeasible = 0 reproduces the reference's "Recovery step is infeasible" (nothing written). */
+int  hdsdpcu_cone_getprimal(void *cone, double dBarrierMu, const double *dRowDual, const double *dRowDualStep,
+                            double *dConePrimal, int *isFeasible);
 /* Hand the cone an S^-1 computed elsewhere (used by the integration shim, whose S factor is owned by the
  * reference's hdsdp_linsys_fp): from a host n x n matrix, or device-to-device from a hdsdpcu_linsys handle
  * (HFpLinsysInvert, linalg/hdsdp_linsolver.c:2120, without the host round trip).  Valid until the next update. */

@@ -118,6 +118,12 @@ int refdrv_ratio_test(refdrv *h, int k, double dTau, const double *dy, double dA
     return (int) HConeRatioTest(h->cones[k], dTau, (double *) dy, dAdaRatio, whichBuffer, maxStep);
 }
 
+/* HConeGetPrimal (interface/hdsdp_conic.c:389 -> sdpDenseConeGetPrimal hdsdp_conic_sdp.c:2395): X = mu (S^-1 + S^-1 dS S^-1),
+ * S = C - A'y, dS = A'dy; X and aux are dim*dim */
+void refdrv_get_primal(refdrv *h, int k, double mu, const double *y, const double *dy, double *X, double *aux) {
+    HConeGetPrimal(h->cones[k], mu, (double *) y, (double *) dy, X, aux);
+}
+
 int refdrv_interior_check(refdrv *h, const double *y, double tau, int *isInterior) {
     int all = 1;
     for (int k = 0; k < h->nCones; ++k) {

@@ -39,6 +39,9 @@ def lib():
         l.refdrv_is_kkt_sparse.argtypes = [c_void_p]
         l.refdrv_set_point.argtypes = [c_void_p, c_double_p, c_double, c_double, c_double_p]
         l.refdrv_interior_check.argtypes = [c_void_p, c_double_p, c_double, c_int_p]
+        if hasattr(l, "refdrv_get_primal"):
+            l.refdrv_get_primal.argtypes = [c_void_p, c_int, c_double, c_double_p, c_double_p, c_double_p, c_double_p]
+            l.refdrv_get_primal.restype = None
         if hasattr(l, "refdrv_ratio_test"):
             l.refdrv_ratio_test.argtypes = [c_void_p, c_int, c_double, c_double_p, c_double, c_int, c_double_p]
         l.refdrv_build.argtypes = [c_void_p, c_int, c_int]
@@ -114,6 +117,13 @@ class RefKKT:
         f = c_int(0)
         self.l.refdrv_interior_check(self.h, _dp(y), float(tau), byref(f))
         return bool(f.value)
+
+    def get_primal(self, k, dim, mu, y, dy) -> np.ndarray:
+        """HConeGetPrimal on cone k (reference primal recovery)."""
+        y = np.ascontiguousarray(y, dtype=np.float64); dy = np.ascontiguousarray(dy, dtype=np.float64)
+        X = np.full((dim, dim), np.nan, order="F"); aux = np.zeros((dim, dim), order="F")
+        self.l.refdrv_get_primal(self.h, int(k), float(mu), _dp(y), _dp(dy), _dp(X), _dp(aux))
+        return X
 
     def ratio_test(self, k, dtau, dy, ada_ratio, which=0) -> float:
         """HConeRatioTest on cone k (reference Lanczos); set_point must have been called."""

@@ -105,3 +105,21 @@ def test_block_cyclic_ownership_arithmetic():
         assert np.array_equal(got, (cols // nb) % P)
         counts = np.bincount((np.arange(50048) // nb) % P, minlength=P)
         assert counts.max() - counts.min() <= nb   # block-cyclic balance
+
+
+def test_binary_container_roundtrip(tmp_path):
+    """the CSC user_data arrays travel as one memory-mappable file (no SDPA text parsing for 50k constraints)."""
+    from hdsdp_b200 import problem
+    for prob in (load_golden("multiblock")[0], problem.gen_theta(60, 300, seed=2)):
+        path = str(tmp_path / "p.hdsdpb")
+        problem.save_bin(prob, path)
+        for mm in (True, False):
+            back = problem.load_bin(path, mmap=mm)
+            assert back.m == prob.m and len(back.cones) == len(prob.cones) and np.array_equal(back.rhs, prob.rhs)
+            for a, b in zip(prob.cones, back.cones):
+                assert a.kind == b.kind and a.dim == b.dim
+                assert np.array_equal(a.beg, b.beg) and np.array_equal(a.idx, b.idx) and np.array_equal(a.elem, b.elem)
+    with open(path, "r+b") as f:
+        f.write(b"X")
+    with pytest.raises(ValueError):
+        problem.load_bin(path)
