@@ -70,11 +70,12 @@ __device__ __forceinline__ bool map_tile(const TileMap &tmap, int bid, int &tm, 
     return true;
 }
 
-// BN = 128: 8 warps (256 threads), one CTA per SM.  BN = 64: 4 warps (128 threads), two CTAs per SM, so one CTA's
+// BN = 128: one CTA per SM.  BN = 64: two CTAs per SM, so one CTA's
 // barrier stalls and C read-modify-write epilogue overlap with the other CTA's main loop.
-template <int BN, int BK, int STAGES, int MINB, bool SIGNED>
-__global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
-    constexpr int NT = BN * 2;
+template <int BN, int BK, int STAGES, int MINB, bool SIGNED, int WM = 64>
+__global__ void __launch_bounds__((128 / WM) * (BN / 32) * 32, MINB) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
+    constexpr int NT = (128 / WM) * (BN / 32) * 32; // warps: (128 / WM) along m x (BN / 32) along n
+    constexpr int MJ = WM / 8;                      // 8-row MMA tiles per warp along m
     constexpr int LDB_ = BN + 4;                          // 132 / 68: both = 4 (mod 16) -> conflict-free fragment loads
     constexpr int STAGE_DOUBLES = BK * (LDS_ + LDB_);     // A tile + B tile
     extern __shared__ __align__(16) double smem[];
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
-    const int wm = (warp & 1) * 64;  // warp offset along m
-    const int wn = (warp >> 1) * 32; // warp offset along n
+    const int wm = (warp % (128 / WM)) * WM; // warp offset along m
+    const int wn = (warp / (128 / WM)) * 32; // warp offset along n
 
     int k_lo = 0;
     if (g.flags & HD_GEMM_KTRI_MAX) k_lo = max(m0, n0) & ~(BK - 1); // X[i,k] == 0 for k < i on both operands
@@ -123,11 +124,11 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
         }
     };
 
-    double acc[4][8][2];
+    double acc[4][MJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < MJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < MJ; ++j)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp + (long) (8 * i) * g.ldc + 8 * j));
         }
     }
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
         const double *Bs = As + BK * LDS_;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            double bf[4], af[8];
+            double bf[4], af[MJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i) bf[i] = Bs[(kk + tig) * LDB_ + wn + 8 * i + gid];
             if (SIGNED) {
@@ -167,11 +168,11 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
                 for (int i = 0; i < 4; ++i) bf[i] *= sg;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) af[j] = As[(kk + tig) * LDS_ + wm + 8 * j + gid];
+            for (int j = 0; j < MJ; ++j) af[j] = As[(kk + tig) * LDS_ + wm + 8 * j + gid];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], bf[i], af[j]);
+                for (int j = 0; j < MJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], bf[i], af[j]);
         }
     }
     cp_async_wait<0>();
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
             for (int i = 0; i < 4; ++i) {
                 const double cs = colscale ? g.alpha * g.sb[n0 + wn + 8 * i + gid] : g.alpha;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < MJ; ++j) {
                     double2 v = make_double2(cs * acc[i][j][0], cs * acc[i][j][1]);
                     *reinterpret_cast<double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j) = v;
                 }
@@ -197,11 +198,11 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
             // read-modify-write in batches of 8 independent 16-byte loads (the C tile was prefetched into L2 above)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                double2 old[8];
+                double2 old[MJ];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) old[j] = *reinterpret_cast<const double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j);
+                for (int j = 0; j < MJ; ++j) old[j] = *reinterpret_cast<const double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < MJ; ++j) {
                     double2 v = make_double2(g.alpha * acc[i][j][0] + g.beta * old[j].x, g.alpha * acc[i][j][1] + g.beta * old[j].y);
                     *reinterpret_cast<double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j) = v;
                 }
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
         const int n = n0 + wn + 8 * i + gid;
         double sbn = hadsq ? g.sb[n] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < MJ; ++j) {
             const int m = m0 + wm + 8 * j + 2 * tig;
             if (lower && m + 1 < n) continue;
             double2 *cp = reinterpret_cast<double2 *>(g.C + (long) n * g.ldc + m);
@@ -243,17 +244,18 @@ __global__ void __launch_bounds__(BN * 2, MINB) dgemm_nt_kernel(GemmArgs g, Tile
 
 int g_num_sms = 0;
 bool g_attr_set = false;
-int g_variant = 3; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x16 4 stages x2 CTAs; 3: 128x64x32 2 stages x2 CTAs
+int g_variant = 4; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x16 4 stages x2 CTAs; 3: 128x64x32 2 stages x2 CTAs;
+                   // 4: as 3 with 8 warps of 32x32 per CTA (16 warps / SM, default); 5: 128x128x32 with 16 warps of 32x32
 
 template <int BN, int BK, int STAGES> constexpr int smem_bytes() { return STAGES * BK * (LDS_ + BN + 4) * 8; }
 
-template <int BN, int BK, int STAGES, int MINB, bool SIGNED = false>
+template <int BN, int BK, int STAGES, int MINB, bool SIGNED = false, int WM = 64>
 int launch_variant(cudaStream_t st, const GemmArgs &g) {
     static unsigned long long attr = 0; // one bit per device (function attributes are per context)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(attr >> (dev & 63) & 1ull)) {
-        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smem_bytes<BN, BK, STAGES>()));
         attr |= 1ull << (dev & 63);
     }
@@ -276,7 +278,7 @@ int launch_variant(cudaStream_t st, const GemmArgs &g) {
     }
     long nblocks = nsuper * GROUP * GN;
     ++g_hd_launches;
-    dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED><<<(unsigned) nblocks, BN * 2, smem_bytes<BN, BK, STAGES>(), st>>>(g, tmap);
+    dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED, WM><<<(unsigned) nblocks, (128 / WM) * (BN / 32) * 32, smem_bytes<BN, BK, STAGES>(), st>>>(g, tmap);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
 }
@@ -313,6 +315,8 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
         case 0: return launch_variant<128, 16, 4, 1>(st, g);
         case 1: return launch_variant<128, 32, 3, 1>(st, g);
         case 2: return launch_variant<64, 16, 4, 2>(st, g);
+        case 4: return launch_variant<64, 32, 2, 2, false, 32>(st, g);  // 8 warps of 32x32, 16 warps / SM
+        case 5: return launch_variant<128, 32, 2, 1, false, 32>(st, g); // 16 warps of 32x32, one CTA / SM
         default: return launch_variant<64, 32, 2, 2>(st, g);
     }
 }
