@@ -288,17 +288,17 @@ __global__ void sparse_vectors_kernel(const double *__restrict__ Sinv, long lds,
     }
 }
 
-// same for constraints with many nonzeros (class SB: e.g. the identity row of the theta problems): one CTA per
-// constraint, one warp per stored entry, deterministic block reduction
+// same for constraints with many nonzeros (class SB: e.g. the identity row of the theta problems): SBV_SPLIT CTAs per
+// constraint, one warp per stored entry, partial sums written to `part` and added in a fixed order (deterministic)
+constexpr int SBV_SPLIT = 32;
 __global__ void __launch_bounds__(256) sparse_vectors_block_kernel(const double *__restrict__ Sinv, long lds, int n,
-                                                                   const int *__restrict__ con, const int *__restrict__ ptr,
-                                                                   const int *__restrict__ row, const int *__restrict__ col,
-                                                                   const double *__restrict__ val, double rd, double *asinv,
-                                                                   double *asinvrd) {
+                                                                   const int *__restrict__ ptr, const int *__restrict__ row,
+                                                                   const int *__restrict__ col, const double *__restrict__ val,
+                                                                   double rd, double *part) {
     __shared__ double r1[8], r2[8];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x, sp = blockIdx.y;
     double s1 = 0.0, s2 = 0.0;
-    for (int e = ptr[c] + w; e < ptr[c + 1]; e += 8) {
+    for (int e = ptr[c] + sp * 8 + w; e < ptr[c + 1]; e += 8 * SBV_SPLIT) {
         const double *cr = Sinv + (long) row[e] * lds;
         const double *cc = Sinv + (long) col[e] * lds;
         if (lane == 0) s1 += val[e] * cr[col[e]];
@@ -315,9 +315,18 @@ __global__ void __launch_bounds__(256) sparse_vectors_block_kernel(const double 
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
         for (int i = 0; i < 8; ++i) { a += r1[i]; b += r2[i]; }
-        asinv[con[c]] += 2.0 * a;
-        if (rd != 0.0) asinvrd[con[c]] += rd * 2.0 * b;
+        part[((long) c * SBV_SPLIT + sp) * 2] = a;
+        part[((long) c * SBV_SPLIT + sp) * 2 + 1] = b;
     }
+}
+__global__ void sparse_vectors_finish_kernel(const double *__restrict__ part, const int *__restrict__ con, int ncon, double rd,
+                                             double *asinv, double *asinvrd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncon) return;
+    double a = 0.0, b = 0.0;
+    for (int sp = 0; sp < SBV_SPLIT; ++sp) { a += part[((long) c * SBV_SPLIT + sp) * 2]; b += part[((long) c * SBV_SPLIT + sp) * 2 + 1]; }
+    asinv[con[c]] += 2.0 * a;
+    if (rd != 0.0) asinvrd[con[c]] += rd * 2.0 * b;
 }
 
 // <A_j, X> for sparse constraints against an explicit symmetric matrix X: one thread per constraint.
@@ -739,7 +748,7 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
 void cone_destroy(ConeCU *c) {
     if (!c) return;
     lz_destroy(c->lanczos);
-    cudaFree(c->d_prim);
+    cudaFree(c->d_prim); cudaFree(c->d_sbv_part);
     cudaFree(c->d_dn_vec); cudaFree(c->d_dn_U); cudaFree(c->d_dn_Ut); cudaFree(c->d_dn_G);
     void *ptrs[] = {c->d_pos, c->d_pos_ptr, c->d_ent_con, c->d_ent_val, c->d_dense_packed, c->d_dense_con, c->d_dr1_F,
                     c->d_dr1_W, c->d_dr1_con, c->d_dr1_sign, c->d_coef, c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_sinv,
@@ -936,9 +945,12 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
         if (c->nss > 0)
             HDK(sparse_vectors_kernel)<<<nblk((long) c->nss * 32, 256), 256, 0, st>>>(Sinv, np, n, c->d_ss_con, c->d_ss_ptr, c->d_ss_row,
                                                                                   c->d_ss_col, c->d_ss_val, c->nss, rd, k->d_asinv, k->d_asinvrd);
-        if (c->nsb > 0)
-            HDK(sparse_vectors_block_kernel)<<<c->nsb, 256, 0, st>>>(Sinv, np, n, c->d_sb_con, c->d_sb_ptr, c->d_sb_row, c->d_sb_col,
-                                                                   c->d_sb_val, rd, k->d_asinv, k->d_asinvrd);
+        if (c->nsb > 0) {
+            if (!c->d_sbv_part) HD_CUDA(cudaMalloc(&c->d_sbv_part, sizeof(double) * 2 * SBV_SPLIT * c->nsb));
+            HDK(sparse_vectors_block_kernel)<<<dim3(c->nsb, SBV_SPLIT), 256, 0, st>>>(Sinv, np, n, c->d_sb_ptr, c->d_sb_row, c->d_sb_col,
+                                                                                    c->d_sb_val, rd, c->d_sbv_part);
+            HDK(sparse_vectors_finish_kernel)<<<nblk(c->nsb, 128), 128, 0, st>>>(c->d_sbv_part, c->d_sb_con, c->nsb, rd, k->d_asinv, k->d_asinvrd);
+        }
         if (c->nd > 0)
             HDK(dense_dot_kernel)<<<c->nd, 256, 0, st>>>(c->d_dn_full, (long) np * np, Sinv, np, n, c->d_dn_con, 0, 0, 1.0, k->d_asinv,
                                                     nullptr, 0, 0, sh);

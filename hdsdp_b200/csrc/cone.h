@@ -98,6 +98,7 @@ struct ConeCU {
     double *d_obj_full = nullptr; // dense / rank-one C expanded to full np x np
 
     double *d_U = nullptr, *d_B = nullptr; // np x np workspaces for explicit S^-1 A S^-1
+    double *d_sbv_part = nullptr;          // partial sums of the many-nnz side vectors
     double *d_prim = nullptr;              // np x np: S^-1 of the checker buffer (primal recovery)
     bool sinv_valid = false;
     LanczosCU *lanczos = nullptr; // ratio-test state (lanczos.cu), created on first use

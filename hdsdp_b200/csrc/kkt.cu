@@ -56,6 +56,17 @@ __global__ void copy_owned_kernel(double *__restrict__ dst, const double *__rest
         dst[(long) col * ld + r] = src[(long) col * ld + r];
 }
 
+// M <- 0 on the part that is ever read: rows >= the first row of each 128-column block, and only the block columns this
+// rank owns (HKKTClean memsets all of M, hdsdp_schur.c:156-162; the strict upper triangle is never referenced)
+__global__ void zero_lower_kernel(double *M, long ld, int mp, int nb, int rank, int nranks) {
+    const int col = blockIdx.y;
+    if (nranks > 1 && (col / nb) % nranks != rank) return;
+    const int r0 = (col / HD_LEAF) * HD_LEAF;
+    double2 *p = reinterpret_cast<double2 *>(M + (long) col * ld + r0);
+    const int cnt = (mp - r0) / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) p[i] = make_double2(0.0, 0.0);
+}
+
 __global__ void add_diag_vec_kernel(double *M, long ld, int m, const double *__restrict__ d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) M[(long) i * ld + i] += d[i];
@@ -150,7 +161,8 @@ int kkt_clean(KktCU *k, int typeKKT) {
     }
     HD_CUDA(cudaMemsetAsync(k->d_scal + 3, 0, sizeof(double), st));
     if (typeKKT == KKT_INFEASIBLE || typeKKT == KKT_HOMOGENEOUS || typeKKT == KKT_PRIMAL) {
-        HD_CUDA(cudaMemsetAsync(k->d_M, 0, sizeof(double) * (size_t) k->mp * k->mp, st));
+        HDK(zero_lower_kernel)<<<dim3(16, k->mp), 256, 0, st>>>(k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
+        HD_CUDA(cudaGetLastError());
         k->factored = false;
         k->fresh = true;
     }
@@ -257,7 +269,9 @@ int kkt_factorize(KktCU *k, int *info_out) {
         k->factored = (rc == HD_OK && info == 0);
         return k->factored ? HD_OK : HD_FAILED;
     }
-    HD_CUDA(cudaMemcpyAsync(k->chol->L, k->d_M, sizeof(double) * (size_t) k->mp * k->mp, cudaMemcpyDeviceToDevice, st));
+    // only the lower trapezoids are ever read by the factorisation: half the traffic of a full copy
+    HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, HD_LEAF, 0, 1);
+    HD_CUDA(cudaGetLastError());
     HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
     int info = 0;
     HD_CALL(chol_factor(st, k->chol, &info));
@@ -266,7 +280,7 @@ int kkt_factorize(KktCU *k, int *info_out) {
         // -- permanently, as HFpLinsysSwitchToIndefinite does.  Here: unpivoted LDL^T with static pivoting on the GPU.
         fprintf(stderr, "[hdsdpcu] KKT system is almost indefinite (pivot %d). Switch to LDL.\n", info);
         k->chol->ldl = true;
-        HD_CUDA(cudaMemcpyAsync(k->chol->L, k->d_M, sizeof(double) * (size_t) k->mp * k->mp, cudaMemcpyDeviceToDevice, st));
+        HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, HD_LEAF, 0, 1);
         HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
         HD_CALL(chol_factor(st, k->chol, &info));
     }
