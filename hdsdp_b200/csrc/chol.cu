@@ -402,6 +402,9 @@ inline double *sgn_of(const double *dinv) {
     return g_ldl ? g_ldl->sgn + ((dinv - g_ldl->dinv_base) / (HD_LEAF * HD_LEAF)) * HD_LEAF : nullptr;
 }
 
+const double *g_peer_local = nullptr;
+double *g_peer_dst = nullptr;
+
 int split_leaves(int n) { return ((n / HD_LEAF) / 2) * HD_LEAF; } // n1 (multiple of 128, >= 128 when n >= 256)
 
 // B (rows x n, ld ldb) <- B * L^-T,  L n x n lower (ld ldl), dinv = inverse leaves of L
@@ -413,6 +416,7 @@ int trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, lo
         g.A = B; g.lda = ldb; g.B = dinv; g.ldb = HD_LEAF; g.C = B; g.ldc = ldb;
         g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
         if (g_ldl) { g.flags = HD_GEMM_EPI_COLSCALE; g.sb = sgn_of(dinv); } // X = (B L^-T) J
+        if (g_peer_dst) g.peerC = g_peer_dst + (B - g_peer_local);
         return hd_gemm_nt(st, g); // in place: each CTA reads exactly the rows it later writes
     }
     int n1 = split_leaves(n), n2 = n - n1;
@@ -488,6 +492,7 @@ int hd_potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int 
 int hd_trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, long ldl, int n, const double *dinv) {
     return trsm_rec(st, B, ldb, rows, L, ldl, n, dinv);
 }
+void hd_trsm_set_peer(const double *local, double *peer) { g_peer_local = local; g_peer_dst = peer; }
 int hd_chol_finish(cudaStream_t st, DenseChol *c) {
     HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);
     HD_CUDA(cudaGetLastError());

@@ -68,6 +68,8 @@ struct GemmArgs {
     int flags;
     const double *sa;   // HADSQ: scale over m
     const double *sb;   // HADSQ: scale over n
+    double *peerC;       // optional second destination with the layout of C (beta == 0, full tiles): the tile is ALSO stored
+                         // there -- a peer GPU's buffer over NVLink (dist.cu: panel solve fused with the hand-off to the next owner)
     const double *ksign; // optional +-1 per k: C = alpha * A diag(ksign) B^T + beta C   (LDL^T updates: A22 -= L21 J L21^T)
     // block-cyclic N (distributed Cholesky, dist.cu): the N dimension enumerates only the column blocks this rank owns.
     // Local column c lives at global column (c / bc_nb) * bc_stride + c % bc_nb (relative to B / C); 0 = contiguous.
@@ -78,7 +80,9 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g);
 // recursive kernels of chol.cu, enqueue-only (used by the single-GPU driver and by dist.cu)
 int hd_potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base);
 int hd_trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, long ldl, int n, const double *dinv);
-int hd_chol_finish(cudaStream_t st, DenseChol *c); // transposed inverse leaves for the L^T solve
+int hd_chol_finish(cudaStream_t st, DenseChol *c);
+// while set, the leaf products of hd_trsm_rec also store their result at peer + (C - local)  (enqueue-time state)
+void hd_trsm_set_peer(const double *local, double *peer); // transposed inverse leaves for the L^T solve
 int hd_num_sms();
 void hd_gemm_set_variant(int v);
 void hd_chol_set_block(int nb);

@@ -15,10 +15,12 @@
 // only that block column, then factors it on a high-priority side stream (recursive potrf + panel trsm, chol.cu)
 // and pushes the panel to the peers while its main stream continues with the rest of its trailing update.
 //
-// Transport.  No collective library on the data path: the owner copies its finished panel straight into the
-// peers' L buffers (IPC-mapped peer memory, copy engines over NVLink / NVSwitch) in ring order starting with the
-// next owner -- the only rank whose critical path waits for it -- and then publishes a sequence number in the
-// peer's control block (st.release.sys).  Consumers wait for that number with a one-thread acquire spin on their
+// Transport.  No collective library on the data path.  The next owner is the only rank whose critical path waits for a
+// panel, so the panel solve is FUSED with the hand-off to it: the epilogue of the triangular-solve GEMM stores every
+// finished tile both locally and, over NVLink, into the next owner's L buffer (IPC-mapped peer memory; GemmArgs::peerC),
+// so the transfer overlaps the math tile by tile and no copy sits on the chain.  The remaining peers (and the small
+// diagonal block / inverse leaves) are served afterwards by the copy engines in ring order.  Each delivery is published
+// as a monotone sequence number in the peer's control block (st.release.sys).  Consumers wait for that number with a one-thread acquire spin on their
 // own GPU (bounded by a timeout).  Ranks that live in the same process are synchronised with CUDA events instead,
 // which is what lets the whole schedule run -- and be tested -- with P ranks on a single GPU.
 #include "common.h"
@@ -35,7 +37,9 @@ constexpr int MAIL_CNT = 8;
 constexpr long long WAIT_TIMEOUT_NS = 30ll * 1000 * 1000 * 1000;
 
 // control block (ints): [0,P) panel sequence from src | [P,2P) ready epoch from src | [2P,3P) info from src |
-//                       [3P,4P) mail sequence from src | [4P] timeout flag
+//                       [3P,4P) mail sequence from src | [4P] timeout flag | [4P+1,5P+1) complete-panel sequence from src
+//   panel sequence    = the part below the diagonal block of panel k has landed (all the factorisation needs)
+//   complete sequence = diagonal block and inverse leaves have landed as well (needed by the solves)
 __device__ __forceinline__ int ld_acquire_sys(const int *p) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -103,7 +107,8 @@ struct DistRank {
     bool own_chol = false, own_stream = false;
     cudaStream_t st = nullptr, side = nullptr, push = nullptr;
     cudaEvent_t ev_col = nullptr, ev_diag = nullptr, ev_panel = nullptr, ev_ready = nullptr;
-    std::vector<cudaEvent_t> ev_recv; // per panel, recorded on the sender's push stream (same-process delivery)
+    std::vector<cudaEvent_t> ev_recv; // per panel, recorded by the sender (same-process delivery): below-diagonal part landed
+    std::vector<cudaEvent_t> ev_full; // ... diagonal block and inverse leaves landed
     char *ctrl = nullptr;
     int *h_ctrl = nullptr;
     struct Peer {
@@ -112,7 +117,8 @@ struct DistRank {
         char *ctrl = nullptr;
         bool ipc = false;
     } peer[MAXP];
-    int ready_epoch_seen[MAXP] = {0};
+    int ready_epoch_seen[MAXP] = {0};      // push stream has waited for the peer's ready flag of this epoch
+    int ready_epoch_seen_side[MAXP] = {0}; // side stream likewise (fused stores)
 };
 
 struct DistChol {
@@ -134,14 +140,18 @@ inline DistRank *local_rank(DistChol *d, int rank) {
 inline int *ctrl_ints(char *c) { return (int *) c; }
 inline int panel_seq(const DistChol *d, int k) { return d->epoch * (d->nblk + 1) + k + 1; }
 
+inline int fused_peer(const DistChol *d, const DistRank *R) { return d->P > 1 ? (R->rank + 1) % d->P : -1; }
+
+// copy engines: whole panel to every peer except the fused one, which only misses the diagonal block; inverse leaves to all
 int push_panel(DistChol *d, DistRank *R, int k) {
     const int P = d->P, nb = d->nb, mp = d->mp;
     const int s0 = k * nb, bk = blk_size(d, k);
     HD_CUDA(cudaStreamWaitEvent(R->push, R->ev_panel, 0));
     const size_t off = (size_t) s0 * mp + s0;
     const size_t leaf_off = (size_t) (s0 / HD_LEAF) * HD_LEAF * HD_LEAF;
+    const int fused = fused_peer(d, R);
     for (int i = 1; i < P; ++i) {
-        const int q = (R->rank + i) % P; // ring order: the next owner (rank + 1) is served first
+        const int q = (R->rank + i) % P; // ring order
         DistRank::Peer &pe = R->peer[q];
         if (R->ready_epoch_seen[q] != d->epoch) {
             // the peer's buffers may still be read by its previous solves: wait until it entered this factorisation
@@ -151,15 +161,19 @@ int push_panel(DistChol *d, DistRank *R, int k) {
         }
         double *dstL = pe.local ? pe.local->chol->L : pe.L;
         double *dstD = pe.local ? pe.local->chol->Dinv : pe.Dinv;
-        HD_CUDA(cudaMemcpy2DAsync(dstL + off, (size_t) mp * 8, R->chol->L + off, (size_t) mp * 8, (size_t) (mp - s0) * 8, bk,
-                                  cudaMemcpyDefault, R->push));
+        const int rows = (q == fused) ? bk : mp - s0; // the fused peer already holds everything below the diagonal block
+        HD_CUDA(cudaMemcpy2DAsync(dstL + off, (size_t) mp * 8, R->chol->L + off, (size_t) mp * 8, (size_t) rows * 8, bk, cudaMemcpyDefault,
+                                  R->push));
         HD_CUDA(cudaMemcpyAsync(dstD + leaf_off, R->chol->Dinv + leaf_off, sizeof(double) * (size_t) (bk / HD_LEAF) * HD_LEAF * HD_LEAF,
                                 cudaMemcpyDefault, R->push));
         if (pe.local) {
-            HD_CUDA(cudaEventRecord(pe.local->ev_recv[k], R->push));
+            if (q != fused) HD_CUDA(cudaEventRecord(pe.local->ev_recv[k], R->push));
+            HD_CUDA(cudaEventRecord(pe.local->ev_full[k], R->push));
         } else {
-            HDK(flag_write_kernel)<<<1, 1, 0, R->push>>>(ctrl_ints(pe.ctrl) + R->rank, panel_seq(d, k), ctrl_ints(pe.ctrl) + 2 * P + R->rank,
-                                                       R->chol->dinfo);
+            if (q != fused)
+                HDK(flag_write_kernel)<<<1, 1, 0, R->push>>>(ctrl_ints(pe.ctrl) + R->rank, panel_seq(d, k), ctrl_ints(pe.ctrl) + 2 * P + R->rank,
+                                                           R->chol->dinfo);
+            HDK(flag_write_kernel)<<<1, 1, 0, R->push>>>(ctrl_ints(pe.ctrl) + 4 * P + 1 + R->rank, panel_seq(d, k), nullptr, nullptr);
         }
     }
     HD_CUDA(cudaGetLastError());
@@ -176,7 +190,25 @@ int factor_panel(DistChol *d, DistRank *R, int k) {
     HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_diag, 0));
     HD_CALL(hd_potrf_rec(R->side, L + (size_t) s * mp + s, mp, b, leaves, R->chol->dinfo, s));
     HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_col, 0));
-    if (below > 0) HD_CALL(hd_trsm_rec(R->side, L + (size_t) s * mp + s + b, mp, below, L + (size_t) s * mp + s, mp, b, leaves));
+    const int fused = fused_peer(d, R);
+    DistRank::Peer *pf = fused >= 0 ? &R->peer[fused] : nullptr;
+    if (pf && R->ready_epoch_seen_side[fused] != d->epoch) {
+        if (pf->local) HD_CUDA(cudaStreamWaitEvent(R->side, pf->local->ev_ready, 0));
+        else HDK(flag_wait_kernel)<<<1, 1, 0, R->side>>>(ctrl_ints(R->ctrl) + d->P + fused, d->epoch, ctrl_ints(R->ctrl) + 4 * d->P);
+        R->ready_epoch_seen_side[fused] = d->epoch;
+    }
+    if (below > 0) {
+        // panel solve fused with the hand-off: every finished tile is also stored into the next owner's buffer
+        if (pf) hd_trsm_set_peer(L, pf->local ? pf->local->chol->L : pf->L);
+        int rc = hd_trsm_rec(R->side, L + (size_t) s * mp + s + b, mp, below, L + (size_t) s * mp + s, mp, b, leaves);
+        hd_trsm_set_peer(nullptr, nullptr);
+        HD_CALL(rc);
+    }
+    if (pf) {
+        if (pf->local) HD_CUDA(cudaEventRecord(pf->local->ev_recv[k], R->side));
+        else HDK(flag_write_kernel)<<<1, 1, 0, R->side>>>(ctrl_ints(pf->ctrl) + R->rank, panel_seq(d, k), ctrl_ints(pf->ctrl) + 2 * d->P + R->rank,
+                                                        R->chol->dinfo);
+    }
     HD_CUDA(cudaEventRecord(R->ev_panel, R->side));
     return push_panel(d, R, k);
 }
@@ -205,8 +237,9 @@ int dist_create(DistChol **pd, int n, int nb, int P, int nlocal, const int *rank
         HD_CUDA(cudaEventCreateWithFlags(&R->ev_diag, cudaEventDisableTiming));
         HD_CUDA(cudaEventCreateWithFlags(&R->ev_panel, cudaEventDisableTiming));
         HD_CUDA(cudaEventCreateWithFlags(&R->ev_ready, cudaEventDisableTiming));
-        R->ev_recv.resize(d->nblk);
+        R->ev_recv.resize(d->nblk); R->ev_full.resize(d->nblk);
         for (auto &e : R->ev_recv) HD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : R->ev_full) HD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         HD_CUDA(cudaMalloc(&R->ctrl, CTRL_BYTES));
         HD_CUDA(cudaMemset(R->ctrl, 0, CTRL_BYTES));
         HD_CUDA(cudaMallocHost(&R->h_ctrl, CTRL_BYTES));
@@ -230,6 +263,7 @@ void dist_destroy(DistChol *d) {
         cudaStreamDestroy(R->side); cudaStreamDestroy(R->push);
         cudaEventDestroy(R->ev_col); cudaEventDestroy(R->ev_diag); cudaEventDestroy(R->ev_panel); cudaEventDestroy(R->ev_ready);
         for (auto &e : R->ev_recv) cudaEventDestroy(e);
+        for (auto &e : R->ev_full) cudaEventDestroy(e);
         cudaFree(R->ctrl); cudaFreeHost(R->h_ctrl);
         delete R;
     }
@@ -377,6 +411,16 @@ int dist_factor(DistChol *d, int *info_out) {
     for (int i = 0; i < d->nlocal; ++i) {
         DistRank *R = d->local[i];
         HD_CUDA(cudaSetDevice(R->dev));
+        // the solves need every diagonal block and inverse leaf: wait for the last complete-panel delivery of each source
+        for (int q = 0; q < P; ++q) {
+            if (q == R->rank) continue;
+            int last = -1;
+            for (int kk = nblk - 1; kk >= 0; --kk)
+                if (kk % P == q) { last = kk; break; }
+            if (last < 0) continue;
+            if (R->peer[q].local) HD_CUDA(cudaStreamWaitEvent(R->st, R->ev_full[last], 0));
+            else HDK(flag_wait_kernel)<<<1, 1, 0, R->st>>>(ctrl_ints(R->ctrl) + 4 * P + 1 + q, panel_seq(d, last), ctrl_ints(R->ctrl) + 4 * P);
+        }
         HD_CALL(hd_chol_finish(R->st, R->chol));
         HD_CUDA(cudaMemcpyAsync(R->chol->hinfo, R->chol->dinfo, sizeof(int), cudaMemcpyDeviceToHost, R->st));
         HD_CUDA(cudaMemcpyAsync(R->h_ctrl, R->ctrl, sizeof(int) * (4 * P + 1), cudaMemcpyDeviceToHost, R->st));

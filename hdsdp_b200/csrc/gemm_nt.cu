@@ -192,6 +192,8 @@ __global__ void __launch_bounds__((128 / WM) * (BN / 32) * 32, MINB) dgemm_nt_ke
                 for (int j = 0; j < MJ; ++j) {
                     double2 v = make_double2(cs * acc[i][j][0], cs * acc[i][j][1]);
                     *reinterpret_cast<double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j) = v;
+                    if (g.peerC) // fused hand-off: the same 16 bytes go to the peer GPU's copy of the panel
+                        *reinterpret_cast<double2 *>(g.peerC + (Cw - g.C) + (long) (8 * i) * g.ldc + 8 * j) = v;
                 }
             }
         } else {
@@ -309,6 +311,7 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
         if (g.N != BN) return HD_FAILED;
         return launch_variant<128, 32, 3, 1>(st, g);
     }
+    if (g.peerC && (g.beta != 0.0 || (g.flags & (HD_GEMM_LOWER | HD_GEMM_EPI_HADSQ)))) return HD_FAILED;
     if ((g.flags & HD_GEMM_EPI_COLSCALE) && (g.beta != 0.0 || (g.flags & (HD_GEMM_LOWER | HD_GEMM_EPI_HADSQ)))) return HD_FAILED;
     if (g.ksign) return launch_variant<64, 32, 2, 2, true>(st, g); // LDL^T fallback path: one instantiation is enough
     switch (g_variant) {
