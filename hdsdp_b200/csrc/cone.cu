@@ -98,14 +98,6 @@ __global__ void add_diag_kernel(double *T, long ld, int n, double v) {
     if (i < n) T[(long) i * ld + i] += v;
 }
 
-__global__ void axpy_lower_kernel(double *dst, const double *src, long ld, int n, double alpha) {
-    long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    long total = (long) n * n;
-    if (idx >= total) return;
-    int i = (int) (idx % n), j = (int) (idx / n);
-    if (i >= j) dst[(long) j * ld + i] += alpha * src[(long) j * ld + i];
-}
-
 // ---------------------------------------------------------------------------------------------
 // Schur kernels
 // ---------------------------------------------------------------------------------------------
@@ -165,16 +157,6 @@ __global__ void r1_vectors_kernel(const double *__restrict__ At, const double *_
     }
     asinv[con[i]] += sign[i] * av;
     if (rd != 0.0) asinvrd[con[i]] += rd * sign[i] * vv;
-}
-
-// out_i += sign_i * sum_r Vt[i,r] * Wt[i,r]  (row-wise dot of two [nrp x np] matrices)
-__global__ void r1_rowdot_kernel(const double *__restrict__ Vt, const double *__restrict__ Wt, long ld, int np, int nr,
-                                 const double *__restrict__ sign, const int *__restrict__ con, double *out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nr) return;
-    double s = 0.0;
-    for (int r = 0; r < np; ++r) s += Vt[(long) r * ld + i] * Wt[(long) r * ld + i];
-    out[con[i]] += sign[i] * s;
 }
 
 // scatter G (nrp x nrp lower) into M through the constraint map: M[ci,cj] += s_i s_j G_ij^2
@@ -616,12 +598,11 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
     if (c->nr > 0) {
         std::vector<double> sg(c->nrp, 0.0);
         std::vector<int> cn(c->nrp, 0), unit(c->nr, -1);
-        bool all_unit = true, any_dense = false;
+        bool all_unit = true;
         for (int k = 0; k < c->nr; ++k) {
             const HostCoeff &h = c->coeff[r_con[k]];
             sg[k] = h.sign; cn[k] = r_con[k];
             if (h.type == COEFF_SPR1 && h.idx.size() == 1 && h.fac[0] == 1.0) unit[k] = h.idx[0]; else all_unit = false;
-            if (h.type == COEFF_DSR1) any_dense = true;
         }
         c->r_all_unit = all_unit;
         c->r_identity_map = (c->nr == m);
@@ -646,7 +627,6 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
             else for (size_t a = 0; a < h.idx.size(); ++a) { sp_idx.push_back(h.idx[a]); sp_val.push_back(h.fac[a]); }
             sp_ptr.push_back((int) sp_idx.size());
         }
-        (void) any_dense;
         HD_CALL(upload(&c->d_r_sp_ptr, sp_ptr)); HD_CALL(upload(&c->d_r_sp_idx, sp_idx)); HD_CALL(upload(&c->d_r_sp_val, sp_val));
         c->r_has_sparse_view = true;
     }
@@ -748,7 +728,7 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
 void cone_destroy(ConeCU *c) {
     if (!c) return;
     lz_destroy(c->lanczos);
-    cudaFree(c->d_prim); cudaFree(c->d_sbv_part);
+    cudaFree(c->d_prim); cudaFree(c->d_sbv_part); cudaFree(c->d_r_G);
     cudaFree(c->d_dn_vec); cudaFree(c->d_dn_U); cudaFree(c->d_dn_Ut); cudaFree(c->d_dn_G);
     void *ptrs[] = {c->d_pos, c->d_pos_ptr, c->d_ent_con, c->d_ent_val, c->d_dense_packed, c->d_dense_con, c->d_dr1_F,
                     c->d_dr1_W, c->d_dr1_con, c->d_dr1_sign, c->d_coef, c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_sinv,
@@ -999,8 +979,8 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
             g.sa = c->d_r_sign; g.sb = c->d_r_sign;
             HD_CALL(hd_gemm_nt(st, g));
         } else {
-            double *G = nullptr;
-            HD_CUDA(cudaMalloc(&G, sizeof(double) * (size_t) c->nrp * c->nrp));
+            if (!c->d_r_G) HD_CUDA(cudaMalloc(&c->d_r_G, sizeof(double) * (size_t) c->nrp * c->nrp)); // kept for the next builds
+            double *G = c->d_r_G;
             GemmArgs g{};
             g.M = c->nrp; g.N = c->nrp; g.K = np;
             g.A = c->d_r_At; g.lda = c->nrp; g.B = c->d_r_Vt; g.ldb = c->nrp; g.C = G; g.ldc = c->nrp;
@@ -1008,8 +988,6 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
             HD_CALL(hd_gemm_nt(st, g));
             int t = (c->nr + 31) / 32;
             HDK(r1_scatter_hadsq_kernel)<<<dim3(t, t), dim3(32, 8), 0, st>>>(G, c->nrp, c->nr, c->d_r_sign, c->d_r_con, k->d_M, ldm, sh);
-            HD_CUDA(cudaStreamSynchronize(st));
-            cudaFree(G);
         }
         HD_CUDA(cudaGetLastError());
     }

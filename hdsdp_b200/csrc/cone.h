@@ -70,6 +70,7 @@ struct ConeCU {
     int *d_r_con = nullptr; double *d_r_sign = nullptr;
     double *d_r_At = nullptr;   // [nrp x np] row i = a_i^T  (column-major, ld nrp)
     double *d_r_Vt = nullptr;   // [nrp x np] workspace V^T = A^T S^-1
+    double *d_r_G = nullptr;    // [nrp x nrp] Gram workspace when R does not map 1:1 onto the Schur rows
     bool r_all_unit = false;    // every factor is a unit vector e_k
     int *d_r_unit = nullptr;    // [nr] k_i when r_all_unit
     bool r_identity_map = false; // R covers constraints 0..m-1 in order

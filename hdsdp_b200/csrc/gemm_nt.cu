@@ -245,7 +245,6 @@ __global__ void __launch_bounds__((128 / WM) * (BN / 32) * 32, MINB) dgemm_nt_ke
 }
 
 int g_num_sms = 0;
-bool g_attr_set = false;
 int g_variant = 4; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x16 4 stages x2 CTAs; 3: 128x64x32 2 stages x2 CTAs;
                    // 4: as 3 with 8 warps of 32x32 per CTA (16 warps / SM, default); 5: 128x128x32 with 16 warps of 32x32
 

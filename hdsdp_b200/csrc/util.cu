@@ -49,15 +49,6 @@ __global__ void symmetrize_kernel(double *A, long lda, int n) {
     }
 }
 
-__global__ void copy2d_kernel(double *dst, long ldd, const double *src, long lds, int rows, int cols) {
-    long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    long total = (long) rows * cols;
-    for (; idx < total; idx += (long) gridDim.x * blockDim.x) {
-        int i = (int) (idx % rows), j = (int) (idx / rows);
-        dst[(long) j * ldd + i] = src[(long) j * lds + i];
-    }
-}
-
 inline unsigned grid_for(long total, int threads) {
     long b = (total + threads - 1) / threads;
     long cap = (long) hd_num_sms() * 16;

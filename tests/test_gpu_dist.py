@@ -42,3 +42,19 @@ def test_distributed_schedule_reports_indefinite_matrix():
     L0 = np.zeros((n, n), order="F")
     rc = lib.hdsdpcu_distchol_selftest(n, nb, P, A.ctypes.data_as(_lib.c_double_p), L0.ctypes.data_as(_lib.c_double_p), None, ctypes.byref(info))
     assert rc == 0 and info.value == 651   # LAPACK dpotrf: 1-based index of the first non-positive pivot
+
+
+def test_multi_process_distributed_schur_on_two_gpus():
+    """One process per GPU over CUDA-IPC peer memory (tools/dist_check.py): distributed assembly + Cholesky + solves must equal
+    the single-GPU KKT object of the same process.  Needs >= 2 GPUs; skipped on the single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29655", os.path.join(root, "tools", "dist_check.py"), "200", "3000", "128"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and '"dist_check": "ok"' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

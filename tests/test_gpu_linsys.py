@@ -144,3 +144,25 @@ def test_indefinite_backend_static_pivot():
     x = ls.solve(b)
     assert np.isfinite(x).all() and np.abs((A @ x - b)[1:]).max() <= 1e-9 * np.abs(b).max()
     ls.close()
+
+
+@pytest.mark.parametrize("leaf,trsv", [(1, 1), (1, 2), (2, 1)])
+def test_alternative_kernel_versions(leaf, trsv):
+    """The measurement knobs (include/hdsdpcu.h hdsdpcu_set_option) select older kernel generations: they must stay correct."""
+    from hdsdp_b200 import _lib
+    from hdsdp_b200.api import DenseLinsys
+    lib = _lib.require_gpu()
+    try:
+        assert lib.hdsdpcu_set_option(b"chol_leaf", leaf) == 0 and lib.hdsdpcu_set_option(b"trsv_version", trsv) == 0
+        n = 700
+        A = spd(n, 77)
+        A = 0.5 * (A + A.T)
+        ls = DenseLinsys(n)
+        assert ls.numeric(np.asfortranarray(A)) == 0
+        np.testing.assert_allclose(ls.get_diag(), np.diag(np.linalg.cholesky(A)), rtol=1e-10)
+        B = np.random.RandomState(2).standard_normal((n, 4))
+        X = ls.solve(B)
+        assert np.abs(X - np.linalg.solve(A, B)).max() <= 1e-9 * np.abs(X).max()
+        ls.close()
+    finally:
+        lib.hdsdpcu_set_option(b"chol_leaf", 2); lib.hdsdpcu_set_option(b"trsv_version", 2)
