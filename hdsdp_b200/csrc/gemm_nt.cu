@@ -72,7 +72,7 @@ __device__ __forceinline__ bool map_tile(const TileMap &tmap, int bid, int &tm, 
 
 // BN = 128: one CTA per SM.  BN = 64: two CTAs per SM, so one CTA's
 // barrier stalls and C read-modify-write epilogue overlap with the other CTA's main loop.
-template <int BN, int BK, int STAGES, int MINB, bool SIGNED, int WM = 64>
+template <int BN, int BK, int STAGES, int MINB, bool SIGNED, int WM = 64, bool PEER = false>
 __global__ void __launch_bounds__((128 / WM) * (BN / 32) * 32, MINB) dgemm_nt_kernel(GemmArgs g, TileMap tmap) {
     constexpr int NT = (128 / WM) * (BN / 32) * 32; // warps: (128 / WM) along m x (BN / 32) along n
     constexpr int MJ = WM / 8;                      // 8-row MMA tiles per warp along m
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__((128 / WM) * (BN / 32) * 32, MINB) dgemm_nt_ke
                 for (int j = 0; j < MJ; ++j) {
                     double2 v = make_double2(cs * acc[i][j][0], cs * acc[i][j][1]);
                     *reinterpret_cast<double2 *>(Cw + (long) (8 * i) * g.ldc + 8 * j) = v;
-                    if (g.peerC) // fused hand-off: the same 16 bytes go to the peer GPU's copy of the panel
+                    if (PEER) // fused hand-off (own instantiation: keeps the pointer out of the register budget of the others): the same 16 bytes go to the peer GPU's copy of the panel
                         *reinterpret_cast<double2 *>(g.peerC + (Cw - g.C) + (long) (8 * i) * g.ldc + 8 * j) = v;
                 }
             }
@@ -250,13 +250,13 @@ int g_variant = 4; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x
 
 template <int BN, int BK, int STAGES> constexpr int smem_bytes() { return STAGES * BK * (LDS_ + BN + 4) * 8; }
 
-template <int BN, int BK, int STAGES, int MINB, bool SIGNED = false, int WM = 64>
+template <int BN, int BK, int STAGES, int MINB, bool SIGNED = false, int WM = 64, bool PEER = false>
 int launch_variant(cudaStream_t st, const GemmArgs &g) {
     static unsigned long long attr = 0; // one bit per device (function attributes are per context)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(attr >> (dev & 63) & 1ull)) {
-        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED, WM, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smem_bytes<BN, BK, STAGES>()));
         attr |= 1ull << (dev & 63);
     }
@@ -279,7 +279,7 @@ int launch_variant(cudaStream_t st, const GemmArgs &g) {
     }
     long nblocks = nsuper * GROUP * GN;
     ++g_hd_launches;
-    dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED, WM><<<(unsigned) nblocks, (128 / WM) * (BN / 32) * 32, smem_bytes<BN, BK, STAGES>(), st>>>(g, tmap);
+    dgemm_nt_kernel<BN, BK, STAGES, MINB, SIGNED, WM, PEER><<<(unsigned) nblocks, (128 / WM) * (BN / 32) * 32, smem_bytes<BN, BK, STAGES>(), st>>>(g, tmap);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
 }
@@ -308,8 +308,10 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
     // owns all columns of its row block: the 64-wide tiles would let a sibling CTA overwrite rows still being read.
     if (g.A == g.C || g.B == g.C) {
         if (g.N != BN) return HD_FAILED;
+        if (g.peerC) return launch_variant<128, 32, 3, 1, false, 64, true>(st, g);
         return launch_variant<128, 32, 3, 1>(st, g);
     }
+    if (g.peerC) return HD_FAILED; // only the in-place leaf products hand their tiles to a peer
     if (g.peerC && (g.beta != 0.0 || (g.flags & (HD_GEMM_LOWER | HD_GEMM_EPI_HADSQ)))) return HD_FAILED;
     if ((g.flags & HD_GEMM_EPI_COLSCALE) && (g.beta != 0.0 || (g.flags & (HD_GEMM_LOWER | HD_GEMM_EPI_HADSQ)))) return HD_FAILED;
     if (g.ksign) return launch_variant<64, 32, 2, 2, true>(st, g); // LDL^T fallback path: one instantiation is enough
