@@ -556,7 +556,7 @@ int chol_load_dev(cudaStream_t st, DenseChol *c, const double *dS, long lds) {
 //   main : [col k+1 -= P_k P_k^T] -> e_col ...... [trailing cols k+2.. -= P_k P_k^T (LOWER)] -> wait e_panel
 //   side :            wait e_col -> potrf(A_{k+1,k+1}) -> A_{k+2..,k+1} <- A L^-T -> e_panel
 static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_ev_col = nullptr, g_ev_panel = nullptr;
+static cudaEvent_t g_ev_col = nullptr, g_ev_panel = nullptr, g_ev_trail = nullptr;
 static int g_lookahead_nb = -1; // block size; 0 disables the blocked path; -1 = by size (measured on B200, tools/probe_block.py)
 
 void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
@@ -583,25 +583,35 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
     mark();
     if (nblk > 1) HD_CALL(trsm_rec(st, A + size(0), lda, np - size(0), A, lda, size(0), leaves(0)));
     mark();
+    // Below ~24k the column update of block k+1 is two latency-bound launches: it runs on the side stream (chained in
+    // front of the panel work it feeds) so that the main stream only ever issues the large trailing GEMMs.  For large
+    // matrices it is real GEMM work that fills the GPU and stays on the main stream.
+    const bool col_on_side = np < 24000;
+    if (!g_ev_trail) HD_CUDA(cudaEventCreateWithFlags(&g_ev_trail, cudaEventDisableTiming));
+    HD_CUDA(cudaEventRecord(g_ev_trail, st));
     for (int k = 0; k + 1 < nblk; ++k) {
         const int s0 = start(k), b0 = size(k), s1 = start(k + 1), b1 = size(k + 1);
         const double *P = A + s0 * lda; // panel k: rows s1.. are the solved block column
+        cudaStream_t cst = col_on_side ? g_side : st;
+        if (col_on_side) HD_CUDA(cudaStreamWaitEvent(g_side, g_ev_trail, 0)); // trailing update k-1 (and panel 0) done
         // (1) update block column k+1: diagonal block (lower tiles) and the rectangle below it
         GemmArgs g{};
         g.M = b1; g.N = b1; g.K = b0;
         g.A = P + s1; g.lda = lda; g.B = P + s1; g.ldb = lda; g.C = A + (long) s1 * lda + s1; g.ldc = lda;
         g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER; g.ksign = sgn_of(leaves(k));
-        HD_CALL(hd_gemm_nt(st, g));
+        HD_CALL(hd_gemm_nt(cst, g));
         const int below = np - (s1 + b1);
         if (below > 0) {
             g.M = below; g.N = b1; g.flags = 0;
             g.A = P + s1 + b1; g.C = A + (long) s1 * lda + s1 + b1;
-            HD_CALL(hd_gemm_nt(st, g));
+            HD_CALL(hd_gemm_nt(cst, g));
         }
-        HD_CUDA(cudaEventRecord(g_ev_col, st));
+        if (!col_on_side) {
+            HD_CUDA(cudaEventRecord(g_ev_col, st));
+            HD_CUDA(cudaStreamWaitEvent(g_side, g_ev_col, 0));
+        }
         mark();
         // (2) side stream: factor block k+1 and solve its panel
-        HD_CUDA(cudaStreamWaitEvent(g_side, g_ev_col, 0));
         HD_CALL(potrf_rec(g_side, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1), info, s1));
         if (below > 0) HD_CALL(trsm_rec(g_side, A + (long) s1 * lda + s1 + b1, lda, below, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1)));
         HD_CUDA(cudaEventRecord(g_ev_panel, g_side));
@@ -612,6 +622,7 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
             g.flags = HD_GEMM_LOWER;
             HD_CALL(hd_gemm_nt(st, g));
         }
+        HD_CUDA(cudaEventRecord(g_ev_trail, st));
         mark();
         HD_CUDA(cudaStreamWaitEvent(st, g_ev_panel, 0));
         mark();
@@ -679,7 +690,7 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
         g_ldl = &ctx;
     }
     int nb = g_lookahead_nb;
-    if (nb < 0) nb = c->np < 12000 ? 256 : (c->np < 24000 ? 512 : (c->np < 40000 ? 1024 : 2048));
+    if (nb < 0) nb = c->np < 24000 ? 256 : (c->np < 40000 ? 1024 : 2048);
     int rc;
     if (nb >= HD_LEAF && c->np >= 4 * nb)
         rc = potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF);

@@ -321,6 +321,8 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
         case 2: return launch_variant<64, 16, 4, 2>(st, g);
         case 4: return launch_variant<64, 32, 2, 2, false, 32>(st, g);  // 8 warps of 32x32, 16 warps / SM
         case 5: return launch_variant<128, 32, 2, 1, false, 32>(st, g); // 16 warps of 32x32, one CTA / SM
+        case 6: return launch_variant<64, 16, 4, 2, false, 32>(st, g);  // as 4 with BK = 16, 4 stages
+        case 7: return launch_variant<64, 16, 3, 2, false, 32>(st, g);  // as 4 with BK = 16, 3 stages
         default: return launch_variant<64, 32, 2, 2>(st, g);
     }
 }

@@ -7,7 +7,10 @@ from hdsdp_b200 import _lib
 lib = _lib.require_gpu(0)
 st = torch.cuda.ExternalStream(lib.hdsdpcu_stream())
 variants = [int(a) for a in sys.argv[1:]] or [3, 4, 5]
-for (M, N, K, lower) in ((32768, 32768, 2048, 1), (8192, 8192, 8192, 0), (16384, 16384, 512, 1), (49152, 512, 512, 0)):
+shapes = ((32768, 32768, 2048, 1), (8192, 8192, 8192, 0), (16384, 16384, 512, 1), (49152, 512, 512, 0))
+if os.environ.get('PROBE_SHAPES') == 'syrk':
+    shapes = shapes[:1] + shapes[2:3]
+for (M, N, K, lower) in shapes:
     A = torch.randn(K, M, dtype=torch.float64, device="cuda"); B = torch.randn(K, N, dtype=torch.float64, device="cuda")
     C = torch.zeros(N, M, dtype=torch.float64, device="cuda")
     ref = None
