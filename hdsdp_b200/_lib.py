@@ -107,7 +107,7 @@ _SIGNATURES = {
     "hdsdpcu_kkt_dist_init": (c_int, [c_void_p, c_int, c_int, c_int]),
     "hdsdpcu_kkt_dist_export": (c_int, [c_void_p, c_void_p]),
     "hdsdpcu_kkt_dist_connect": (c_int, [c_void_p, c_void_p]),
-    "hdsdpcu_distchol_selftest": (c_int, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
+    "hdsdpcu_distchol_selftest": (c_int, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p, c_int_p, c_int, c_double_p]),
     "hdsdpcu_dgemm_nt_dev": (c_int, [c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double, c_void_p, c_long, c_int]),
 }
 

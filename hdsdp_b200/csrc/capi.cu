@@ -547,7 +547,8 @@ int hdsdpcu_kkt_dist_connect(void *kkt, const void *blobs) {
 // The whole distributed schedule with nRanks ranks living in this process on the current device (CUDA events
 // instead of peer flags): rank r gets only the block columns it owns (the rest of its buffer is poisoned with NaN),
 // every rank must end up with the complete factor.  outL[r] (n x n, lower meaningful) for r = 0 and nRanks-1.
-int hdsdpcu_distchol_selftest(int n, int blockSize, int nRanks, const double *A, double *outL0, double *outLlast, int *info) {
+int hdsdpcu_distchol_selftest(int n, int blockSize, int nRanks, const double *A, double *outL0, double *outLlast, int *info,
+                              int indefinite, double *outSign0) {
     HD_CALL(ensure_ready());
     if (nRanks < 1 || nRanks > 16) return HD_FAILED;
     DistChol *d = nullptr;
@@ -569,7 +570,9 @@ int hdsdpcu_distchol_selftest(int n, int blockSize, int nRanks, const double *A,
         }
         if (cudaMemcpy(c->L, stage.data(), sizeof(double) * (size_t) np * np, cudaMemcpyHostToDevice) != cudaSuccess) rc = HD_FAILED;
     }
-    if (rc == HD_OK) rc = dist_factor(d, info);
+    if (rc == HD_OK) rc = dist_factor(d, info, indefinite != 0);
+    if (rc == HD_OK && indefinite && outSign0 &&
+        cudaMemcpy(outSign0, dist_local_chol(d, 0)->sgn, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = HD_FAILED;
     for (int pass = 0; pass < 2 && rc == HD_OK; ++pass) {
         double *out = pass == 0 ? outL0 : outLlast;
         if (!out) continue;

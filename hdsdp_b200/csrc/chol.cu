@@ -493,6 +493,13 @@ int hd_trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L,
     return trsm_rec(st, B, ldb, rows, L, ldl, n, dinv);
 }
 void hd_trsm_set_peer(const double *local, double *peer) { g_peer_local = local; g_peer_dst = peer; }
+// LDL^T mode for the enqueue calls that follow (dist.cu drives hd_potrf_rec / hd_trsm_rec itself); c == nullptr ends it
+void hd_ldl_scope(DenseChol *c) {
+    static LdlCtx ctx;
+    if (!c) { g_ldl = nullptr; return; }
+    ctx.sgn = c->sgn; ctx.dinv_base = c->Dinv; ctx.floorp = c->dfloor; ctx.nperturb = c->dperturb;
+    g_ldl = &ctx;
+}
 int hd_chol_finish(cudaStream_t st, DenseChol *c) {
     HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);
     HD_CUDA(cudaGetLastError());
@@ -507,7 +514,8 @@ int chol_create(DenseChol **pc, int n) {
     c->np = hd_pad(n);
     size_t bytes = (size_t) c->np * c->np * sizeof(double);
     if (cudaMalloc(&c->L, bytes) != cudaSuccess) { free(c); cudaGetLastError(); return HD_MEMORY; }
-    if (cudaMalloc(&c->Dinv, (size_t) c->np * HD_LEAF * sizeof(double)) != cudaSuccess) {
+    // inverse leaves, followed by the np sign entries of the LDL^T mode (one allocation: one IPC handle covers both)
+    if (cudaMalloc(&c->Dinv, ((size_t) c->np * HD_LEAF + c->np) * sizeof(double)) != cudaSuccess) {
         cudaFree(c->L); free(c); cudaGetLastError(); return HD_MEMORY;
     }
     if (cudaMalloc(&c->DinvT, (size_t) c->np * HD_LEAF * sizeof(double)) != cudaSuccess ||
@@ -517,6 +525,7 @@ int chol_create(DenseChol **pc, int n) {
     if (cudaMalloc(&c->dinfo, sizeof(int)) != cudaSuccess || cudaMallocHost(&c->hinfo, sizeof(int)) != cudaSuccess) {
         cudaFree(c->L); cudaFree(c->Dinv); free(c); cudaGetLastError(); return HD_MEMORY;
     }
+    c->sgn = c->Dinv + (size_t) c->np * HD_LEAF;
     c->work = nullptr;
     c->factored = false;
     *pc = c;
@@ -532,7 +541,7 @@ void chol_destroy(DenseChol *c) {
     cudaFree(c->dinfo);
     cudaFreeHost(c->hinfo);
     if (c->work) cudaFree(c->work);
-    if (c->sgn) { cudaFree(c->sgn); cudaFree(c->dfloor); cudaFree(c->dperturb); }
+    if (c->dfloor) { cudaFree(c->dfloor); cudaFree(c->dperturb); }
     free(c);
 }
 
@@ -650,10 +659,11 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
 }
 
 namespace {
-__global__ void ldl_floor_kernel(const double *A, long ld, int n, double *floorp, int *nperturb) {
+__global__ void ldl_floor_kernel(const double *A, long ld, int n, double *floorp, int *nperturb, int nb, int rank, int nranks) {
     __shared__ double red[256];
     double v = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) v = fmax(v, fabs(A[(long) i * ld + i]));
+    for (int i = threadIdx.x; i < n; i += 256)
+        if (nranks <= 1 || (i / nb) % nranks == rank) v = fmax(v, fabs(A[(long) i * ld + i])); // only owned columns hold the matrix
     red[threadIdx.x] = v;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -673,6 +683,17 @@ __global__ void count_negative_kernel(const double *__restrict__ sgn, int n, int
 }
 } // namespace
 
+// allocate the LDL state on first use and set the static-pivoting floor from the (owned part of the) diagonal in c->L
+int chol_ldl_prepare(cudaStream_t st, DenseChol *c, int nb, int rank, int nranks) {
+    if (!c->dfloor) {
+        HD_CUDA(cudaMalloc(&c->dfloor, sizeof(double)));
+        HD_CUDA(cudaMalloc(&c->dperturb, 2 * sizeof(int)));
+    }
+    HDK(ldl_floor_kernel)<<<1, 256, 0, st>>>(c->L, c->np, c->n, c->dfloor, c->dperturb, nb, rank, nranks);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
 // Cholesky (c->ldl == false; *info = LAPACK dpotrf info) or LDL^T with unit-magnitude D (c->ldl == true; always
 // "succeeds": *info = 0, c->nperturbed / c->nnegative report the static pivots and the inertia)
 int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
@@ -680,12 +701,7 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
     LdlCtx ctx{};
     if (c->ldl) {
-        if (!c->sgn) {
-            HD_CUDA(cudaMalloc(&c->sgn, sizeof(double) * c->np));
-            HD_CUDA(cudaMalloc(&c->dfloor, sizeof(double)));
-            HD_CUDA(cudaMalloc(&c->dperturb, 2 * sizeof(int)));
-        }
-        HDK(ldl_floor_kernel)<<<1, 256, 0, st>>>(c->L, c->np, c->n, c->dfloor, c->dperturb);
+        HD_CALL(chol_ldl_prepare(st, c, HD_LEAF, 0, 1));
         ctx.sgn = c->sgn; ctx.dinv_base = c->Dinv; ctx.floorp = c->dfloor; ctx.nperturb = c->dperturb;
         g_ldl = &ctx;
     }

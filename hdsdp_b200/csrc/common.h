@@ -82,7 +82,9 @@ int hd_potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int 
 int hd_trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, long ldl, int n, const double *dinv);
 int hd_chol_finish(cudaStream_t st, DenseChol *c);
 // while set, the leaf products of hd_trsm_rec also store their result at peer + (C - local)  (enqueue-time state)
-void hd_trsm_set_peer(const double *local, double *peer); // transposed inverse leaves for the L^T solve
+void hd_trsm_set_peer(const double *local, double *peer);
+void hd_ldl_scope(DenseChol *c);
+int chol_ldl_prepare(cudaStream_t st, DenseChol *c, int nb, int rank, int nranks); // transposed inverse leaves for the L^T solve
 int hd_num_sms();
 void hd_gemm_set_variant(int v);
 void hd_chol_set_block(int nb);
@@ -106,7 +108,7 @@ struct DenseChol {
     bool factored;
     // LDL^T fallback (reference dsytrf path): A = L J L^T, J = diag(sgn); allocated on first use
     bool ldl;
-    double *sgn;     // np entries, +-1
+    double *sgn;     // np entries, +-1 (stored behind the inverse leaves in the Dinv allocation)
     double *dfloor;  // device scalar: static-pivoting floor = 1e-13 max|diag A|
     int *dperturb;   // device: number of pivots replaced by the floor
     int nperturbed, nnegative;

@@ -134,7 +134,7 @@ cudaStream_t dist_local_stream(DistChol *d, int li);
 int dist_block(const DistChol *d);
 int dist_export(DistChol *d, int li, void *blob);   // 192 bytes
 int dist_connect(DistChol *d, const void *blobs);    // P x 192 bytes, rank order
-int dist_factor(DistChol *d, int *info_out);
+int dist_factor(DistChol *d, int *info_out, bool ldl = false);
 int dist_allgather_small(DistChol *d, const double *d_val, int cnt, double *d_out);
 
 int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx, const double *elem);

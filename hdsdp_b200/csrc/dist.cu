@@ -113,7 +113,7 @@ struct DistRank {
     int *h_ctrl = nullptr;
     struct Peer {
         DistRank *local = nullptr;
-        double *L = nullptr, *Dinv = nullptr;
+        double *L = nullptr, *Dinv = nullptr, *sgn = nullptr;
         char *ctrl = nullptr;
         bool ipc = false;
     } peer[MAXP];
@@ -166,6 +166,8 @@ int push_panel(DistChol *d, DistRank *R, int k) {
                                   R->push));
         HD_CUDA(cudaMemcpyAsync(dstD + leaf_off, R->chol->Dinv + leaf_off, sizeof(double) * (size_t) (bk / HD_LEAF) * HD_LEAF * HD_LEAF,
                                 cudaMemcpyDefault, R->push));
+        if (R->chol->ldl && q != fused)
+            HD_CUDA(cudaMemcpyAsync((pe.local ? pe.local->chol->sgn : pe.sgn) + s0, R->chol->sgn + s0, sizeof(double) * bk, cudaMemcpyDefault, R->push));
         if (pe.local) {
             if (q != fused) HD_CUDA(cudaEventRecord(pe.local->ev_recv[k], R->push));
             HD_CUDA(cudaEventRecord(pe.local->ev_full[k], R->push));
@@ -188,7 +190,11 @@ int factor_panel(DistChol *d, DistRank *R, int k) {
     double *L = R->chol->L;
     double *leaves = R->chol->Dinv + (size_t) (s / HD_LEAF) * HD_LEAF * HD_LEAF;
     HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_diag, 0));
-    HD_CALL(hd_potrf_rec(R->side, L + (size_t) s * mp + s, mp, b, leaves, R->chol->dinfo, s));
+    const bool ldl = R->chol->ldl;
+    if (ldl) hd_ldl_scope(R->chol);
+    int prc = hd_potrf_rec(R->side, L + (size_t) s * mp + s, mp, b, leaves, R->chol->dinfo, s);
+    hd_ldl_scope(nullptr);
+    HD_CALL(prc);
     HD_CUDA(cudaStreamWaitEvent(R->side, R->ev_col, 0));
     const int fused = fused_peer(d, R);
     DistRank::Peer *pf = fused >= 0 ? &R->peer[fused] : nullptr;
@@ -200,10 +206,14 @@ int factor_panel(DistChol *d, DistRank *R, int k) {
     if (below > 0) {
         // panel solve fused with the hand-off: every finished tile is also stored into the next owner's buffer
         if (pf) hd_trsm_set_peer(L, pf->local ? pf->local->chol->L : pf->L);
+        if (ldl) hd_ldl_scope(R->chol);
         int rc = hd_trsm_rec(R->side, L + (size_t) s * mp + s + b, mp, below, L + (size_t) s * mp + s, mp, b, leaves);
         hd_trsm_set_peer(nullptr, nullptr);
+        hd_ldl_scope(nullptr);
         HD_CALL(rc);
     }
+    if (pf && ldl) // the next owner needs the signs of this panel for its column update
+        HD_CUDA(cudaMemcpyAsync((pf->local ? pf->local->chol->sgn : pf->sgn) + s, R->chol->sgn + s, sizeof(double) * b, cudaMemcpyDefault, R->side));
     if (pf) {
         if (pf->local) HD_CUDA(cudaEventRecord(pf->local->ev_recv[k], R->side));
         else HDK(flag_write_kernel)<<<1, 1, 0, R->side>>>(ctrl_ints(pf->ctrl) + R->rank, panel_seq(d, k), ctrl_ints(pf->ctrl) + 2 * d->P + R->rank,
@@ -297,6 +307,7 @@ int dist_connect(DistChol *d, const void *blobs) {
             HD_CUDA(cudaIpcOpenMemHandle(&p1, h[3 * q + 1], cudaIpcMemLazyEnablePeerAccess));
             HD_CUDA(cudaIpcOpenMemHandle(&p2, h[3 * q + 2], cudaIpcMemLazyEnablePeerAccess));
             R->peer[q].L = (double *) p0; R->peer[q].Dinv = (double *) p1; R->peer[q].ctrl = (char *) p2;
+            R->peer[q].sgn = R->peer[q].Dinv + (size_t) d->mp * HD_LEAF; // sign entries follow the inverse leaves (chol_create)
             R->peer[q].ipc = true;
         }
     }
@@ -306,7 +317,8 @@ int dist_connect(DistChol *d, const void *blobs) {
 
 // Factor.  On entry the block columns owned by each local rank hold M (lower part, rows >= the block's first row,
 // identity padded); on exit every local rank's buffer holds the complete factor and all inverse leaves.
-int dist_factor(DistChol *d, int *info_out) {
+// ldl: unpivoted L J L^T (signed Cholesky, chol.cu) instead of Cholesky; the sign vector travels with the panels
+int dist_factor(DistChol *d, int *info_out, bool ldl) {
     if (!d->connected) return HD_FAILED;
     d->epoch++;
     const int P = d->P, nb = d->nb, mp = d->mp, nblk = d->nblk;
@@ -315,6 +327,8 @@ int dist_factor(DistChol *d, int *info_out) {
         DistRank *R = d->local[i];
         HD_CUDA(cudaSetDevice(R->dev));
         HD_CUDA(cudaMemsetAsync(R->chol->dinfo, 0, sizeof(int), R->st));
+        R->chol->ldl = ldl;
+        if (ldl) HD_CALL(chol_ldl_prepare(R->st, R->chol, nb, R->rank, P));
         HD_CUDA(cudaEventRecord(R->ev_ready, R->st));
         HD_CUDA(cudaEventRecord(R->ev_diag, R->st));
         HD_CUDA(cudaEventRecord(R->ev_col, R->st));
@@ -362,6 +376,7 @@ int dist_factor(DistChol *d, int *info_out) {
             g.M = b1; g.N = b1; g.K = bk;
             g.A = Pk + s1; g.lda = mp; g.B = Pk + s1; g.ldb = mp; g.C = R->chol->L + (size_t) s1 * mp + s1; g.ldc = mp;
             g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+            if (ldl) g.ksign = R->chol->sgn + s0;
             HD_CALL(hd_gemm_nt(R->st, g));
             HD_CUDA(cudaEventRecord(R->ev_diag, R->st));
             const int below = mp - s1 - b1;
@@ -387,6 +402,7 @@ int dist_factor(DistChol *d, int *info_out) {
             g.M = mp - ms; g.N = cnt * nb; g.K = bk;
             g.A = Pk + ms; g.lda = mp; g.B = Pk + ms; g.ldb = mp; g.C = R->chol->L + (size_t) ms * mp + ms; g.ldc = mp;
             g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+            if (ldl) g.ksign = R->chol->sgn + s0;
             g.bc_nb = nb; g.bc_stride = P * nb;
             HD_CALL(hd_gemm_nt(R->st, g));
         }

@@ -264,7 +264,14 @@ int kkt_factorize(KktCU *k, int *info_out) {
         HD_CUDA(cudaGetLastError());
         HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
         int info = 0;
-        int rc = dist_factor(k->dist, &info);
+        int rc = dist_factor(k->dist, &info, k->chol->ldl);
+        if (rc == HD_OK && info > 0 && !k->chol->ldl) {
+            // every rank sees the same info (it travels with the panels): all switch to LDL^T together, for good
+            fprintf(stderr, "[hdsdpcu] KKT system is almost indefinite (pivot %d). Switch to LDL.\n", info);
+            HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
+            HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
+            rc = dist_factor(k->dist, &info, true);
+        }
         if (info_out) *info_out = info;
         k->factored = (rc == HD_OK && info == 0);
         return k->factored ? HD_OK : HD_FAILED;

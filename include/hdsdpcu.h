@@ -201,8 +201,10 @@ int  hdsdpcu_dist_owner(int col, int blockSize, int nRanks);   /* pure host arit
 int  hdsdpcu_kkt_dist_init(void *kkt, int rank, int nRanks, int blockSize);
 int  hdsdpcu_kkt_dist_export(void *kkt, void *blob);
 int  hdsdpcu_kkt_dist_connect(void *kkt, const void *blobs /* nRanks blobs, rank order */);
-/* test hook: the same schedule with nRanks ranks inside this process on one GPU (events instead of peer flags) */
-int  hdsdpcu_distchol_selftest(int n, int blockSize, int nRanks, const double *A, double *outL0, double *outLlast, int *info);
+/* test hook: the same schedule with nRanks ranks inside this process on one GPU (events instead of peer flags);
+ * indefinite != 0: the LDL^T mode (A = L J L^T), outSign0 = diag(J) as seen by rank 0 */
+int  hdsdpcu_distchol_selftest(int n, int blockSize, int nRanks, const double *A, double *outL0, double *outLlast, int *info,
+                               int indefinite, double *outSign0);
 
 /* ---------------------------------------------------------------------------------------------
  * Stand-alone kernels exposed for tests and roofline measurement

@@ -24,7 +24,7 @@ def test_distributed_schedule_matches_lapack(n, nb, P):
     L1 = np.zeros((n, n), order="F")
     info = ctypes.c_int(-1)
     rc = lib.hdsdpcu_distchol_selftest(n, nb, P, A.ctypes.data_as(_lib.c_double_p), L0.ctypes.data_as(_lib.c_double_p),
-                                       L1.ctypes.data_as(_lib.c_double_p), ctypes.byref(info))
+                                       L1.ctypes.data_as(_lib.c_double_p), ctypes.byref(info), 0, None)
     assert rc == 0 and info.value == 0
     ref = np.linalg.cholesky(A)
     for L in (L0, L1):
@@ -40,8 +40,28 @@ def test_distributed_schedule_reports_indefinite_matrix():
     A[650, 650] = -1.0
     info = ctypes.c_int(0)
     L0 = np.zeros((n, n), order="F")
-    rc = lib.hdsdpcu_distchol_selftest(n, nb, P, A.ctypes.data_as(_lib.c_double_p), L0.ctypes.data_as(_lib.c_double_p), None, ctypes.byref(info))
+    rc = lib.hdsdpcu_distchol_selftest(n, nb, P, A.ctypes.data_as(_lib.c_double_p), L0.ctypes.data_as(_lib.c_double_p), None, ctypes.byref(info), 0, None)
     assert rc == 0 and info.value == 651   # LAPACK dpotrf: 1-based index of the first non-positive pivot
+
+
+@pytest.mark.parametrize("n,nb,P,nneg", [(900, 128, 3, 11), (2100, 256, 4, 300), (1300, 512, 2, 1)])
+def test_distributed_ldl_mode(n, nb, P, nneg):
+    """The LDL^T fallback through the distributed schedule: A = L J L^T on every rank, signs travel with the panels."""
+    lib = _lib.require_gpu()
+    rs = np.random.RandomState(n)
+    d = np.concatenate([-rs.uniform(1.0, 3.0, nneg), rs.uniform(1.0, 3.0, n - nneg)]); rs.shuffle(d)
+    E = rs.standard_normal((n, n)) * (0.2 / np.sqrt(n))
+    A = np.asfortranarray(np.diag(d) + 0.5 * (E + E.T))
+    L0 = np.zeros((n, n), order="F"); L1 = np.zeros((n, n), order="F"); sg = np.zeros(n)
+    info = ctypes.c_int(-1)
+    rc = lib.hdsdpcu_distchol_selftest(n, nb, P, A.ctypes.data_as(_lib.c_double_p), L0.ctypes.data_as(_lib.c_double_p),
+                                       L1.ctypes.data_as(_lib.c_double_p), ctypes.byref(info), 1, sg.ctypes.data_as(_lib.c_double_p))
+    assert rc == 0 and info.value == 0
+    assert set(np.unique(sg)) <= {-1.0, 1.0} and int((sg < 0).sum()) == int((np.linalg.eigvalsh(A) < 0).sum())
+    for L in (L0, L1):
+        T = np.tril(L)
+        assert np.isfinite(T).all()
+        assert np.abs((T * sg) @ T.T - A).max() <= 1e-11 * np.abs(A).max() * n
 
 
 def test_multi_process_distributed_schur_on_two_gpus():
