@@ -49,6 +49,24 @@ for it in range(3):
     e.append(np.abs(a0 - a1).max() / np.abs(a0).max()); e.append(np.abs(b0 - b1).max() / np.abs(b0).max())
     worst = max(worst, max(e))
     print(json.dumps({"rank": rank, "it": it, "errs": [float(x) for x in e]}), flush=True)
+# LDL^T fallback across processes: shift the diagonal so that a few eigenvalues go negative on BOTH objects
+if os.environ.get("DIST_CHECK_LDL", "1") == "1":
+    y = bench.theta_point(prob.m, n, 7)
+    cone.update(bench.TAU, y); assert cone.factorize()
+    sols = []
+    for k in (ref, kkt):
+        k.build_up(api.KKT_TYPE_INFEASIBLE)
+        if k is ref:
+            M = np.tril(k.get_matrix()); M = M + np.tril(M, -1).T
+            lam = np.linalg.eigvalsh(M); shift = 0.5 * (lam[3] + lam[4])
+        k.build_up_extra_bound(-shift * np.ones(prob.m), np.zeros(prob.m))
+        assert k.factorize() == 0
+        sols.append(k.solve(prob.rhs))
+    e = float(np.abs(sols[0] - sols[1]).max() / np.abs(sols[0]).max())
+    truth = np.linalg.solve(M - shift * np.eye(prob.m), prob.rhs)
+    e2 = float(np.abs(sols[1] - truth).max() / np.abs(truth).max())
+    print(json.dumps({"rank": rank, "ldl_dist_vs_single": e, "ldl_dist_vs_numpy": e2}), flush=True)
+    worst = max(worst, e, e2 * 1e-2)
 t = torch.tensor([worst], device="cuda", dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
