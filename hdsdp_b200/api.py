@@ -166,6 +166,12 @@ class SDPCone:
         check(self.lib.hdsdpcu_cone_ratiotest(self.h, float(dtau), _dp(dy), float(ada_ratio), int(which), byref(step)), "HConeRatioTest")
         return step.value
 
+    def build_primal_xsx(self, X: np.ndarray, XSX: np.ndarray, dual_mat: int = 1) -> np.ndarray:
+        """HConeBuildPrimalXSXDirection: returns XSX + X S X."""
+        X = np.asfortranarray(X, dtype=np.float64); out = np.asfortranarray(XSX, dtype=np.float64).copy(order="F")
+        check(self.lib.hdsdpcu_cone_buildprimalxsx(self.h, _dp(X), _dp(out), int(dual_mat)), "HConeBuildPrimalXSXDirection")
+        return out
+
     def get_primal(self, mu: float, y: np.ndarray, dy: np.ndarray):
         """HConeGetPrimal: X = mu (S^-1 + S^-1 dS S^-1) with S = C - A'y, dS = A'dy; None if S is not positive definite."""
         y = np.ascontiguousarray(y, dtype=np.float64); dy = np.ascontiguousarray(dy, dtype=np.float64)

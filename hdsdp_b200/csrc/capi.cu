@@ -353,6 +353,9 @@ int hdsdpcu_cone_scal(void *cone, double dScal) {
     return HD_OK;
 }
 
+int hdsdpcu_cone_buildprimalxsx(void *cone, const double *dPrimalScalMatrix, double *dPrimalXSXBuffer, int iDualMat) {
+    return cone_build_xsx((ConeCU *) cone, dPrimalScalMatrix, dPrimalXSXBuffer, iDualMat);
+}
 int hdsdpcu_cone_getprimal(void *cone, double dBarrierMu, const double *dRowDual, const double *dRowDualStep, double *dConePrimal, int *isFeasible) {
     return cone_get_primal((ConeCU *) cone, dBarrierMu, dRowDual, dRowDualStep, dConePrimal, isFeasible);
 }

@@ -879,6 +879,46 @@ int cone_get_primal(ConeCU *c, double mu, const double *yHost, const double *dyH
     return HD_OK;
 }
 
+// Primal direction of the PSDP refinement (reference coneBuildPrimalDirection = sdpDenseConeBuildPrimalXSXDirection,
+// hdsdp_conic_sdp.c:2021-2040, fds_trimultiply linalg/dense_opts.c:102): XSX += X S X with S = the dual matrix
+// (iDualMat != 0) or the dual step buffer; X and XSX are host n x n full symmetric matrices.
+__global__ void xsx_accumulate_kernel(const double *__restrict__ R, double *acc, long ld, int n) {
+    const int i = blockIdx.x * 32 + threadIdx.x, j0 = blockIdx.y * 32;
+    if (i >= n) return;
+    for (int jj = threadIdx.y; jj < 32; jj += 8) {
+        const int j = j0 + jj;
+        if (j >= n) continue;
+        // the reference adds the same dot product to (i, j) and (j, i): keep the result exactly symmetric
+        acc[(long) j * ld + i] += (i >= j) ? R[(long) j * ld + i] : R[(long) i * ld + j];
+    }
+}
+
+int cone_build_xsx(ConeCU *c, const double *Xhost, double *XSXhost, int iDualMat) {
+    cudaStream_t st = hd_stream();
+    const int n = c->n, np = c->np;
+    const int which = iDualMat ? BUF_DUALVAR : BUF_DUALSTEP;
+    HD_CALL(ensure_UB(c));
+    if (!c->d_prim) HD_CUDA(cudaMalloc(&c->d_prim, sizeof(double) * (size_t) np * np));
+    HD_CALL(hd_symmetrize_lower(st, c->d_buf[which], np, np));     // the strict upper triangle of the buffers is never read elsewhere
+    double *X = c->d_prim;
+    HD_CUDA(cudaMemsetAsync(X, 0, sizeof(double) * (size_t) np * np, st));
+    HD_CUDA(cudaMemcpy2DAsync(X, (size_t) np * 8, Xhost, (size_t) n * 8, (size_t) n * 8, n, cudaMemcpyHostToDevice, st));
+    GemmArgs g{};
+    g.M = np; g.N = np; g.K = np; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
+    g.A = X; g.lda = np; g.B = c->d_buf[which]; g.ldb = np; g.C = c->d_U; g.ldc = np;    // U = X S
+    HD_CALL(hd_gemm_nt(st, g));
+    g.A = c->d_U; g.B = X; g.C = c->d_B;                                                  // R = U X
+    HD_CALL(hd_gemm_nt(st, g));
+    // accumulate into the caller's buffer on the device (one more n^2 each way keeps the += exact)
+    HD_CUDA(cudaMemcpy2DAsync(c->d_U, (size_t) np * 8, XSXhost, (size_t) n * 8, (size_t) n * 8, n, cudaMemcpyHostToDevice, st));
+    int t = (n + 31) / 32;
+    HDK(xsx_accumulate_kernel)<<<dim3(t, t), dim3(32, 8), 0, st>>>(c->d_B, c->d_U, np, n);
+    HD_CUDA(cudaGetLastError());
+    HD_CUDA(cudaMemcpy2DAsync(XSXhost, (size_t) n * 8, c->d_U, (size_t) np * 8, (size_t) n * 8, n, cudaMemcpyDeviceToHost, st));
+    HD_CUDA(cudaStreamSynchronize(st));
+    return HD_OK;
+}
+
 // U_i = A_i Sinv for ALL dense rows in one GEMM: rows (i, c) of the vec layout are an affine index, K = k
 static int dd_compute_U(ConeCU *c, cudaStream_t st) {
     GemmArgs g{};

@@ -131,6 +131,9 @@ int  hdsdpcu_cone_lanczossteps(void *cone);
 /* Primal recovery.  conePRecover = sdpDenseConeGetPrimal (hdsdp_conic_sdp.c:2395-2446): with S = C - A'y
  * (checked for positive definiteness in BUFFER_DUALCHECK) and dS = A'dy, dConePrimal (n x n, column-major, full symmetric)
  * = mu (S^-1 + S^-1 dS S^-1).  *isFeasible = 0 reproduces the reference's "Recovery step is infeasible" (nothing written). */
+/* coneBuildPrimalDirection = sdpDenseConeBuildPrimalXSXDirection (hdsdp_conic_sdp.c:2021, fds_trimultiply dense_opts.c:102), used by
+ * the PSDP primal refinement: dPrimalXSXBuffer += X S X, S = BUFFER_DUALVAR (iDualMat != 0) or BUFFER_DUALSTEP; host n x n matrices. */
+int  hdsdpcu_cone_buildprimalxsx(void *cone, const double *dPrimalScalMatrix, double *dPrimalXSXBuffer, int iDualMat);
 int  hdsdpcu_cone_getprimal(void *cone, double dBarrierMu, const double *dRowDual, const double *dRowDualStep,
                             double *dConePrimal, int *isFeasible);
 /* Hand the cone an S^-1 computed elsewhere (used by the integration shim, whose S factor is owned by the

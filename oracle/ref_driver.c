@@ -124,6 +124,12 @@ void refdrv_get_primal(refdrv *h, int k, double mu, const double *y, const doubl
     HConeGetPrimal(h->cones[k], mu, (double *) y, (double *) dy, X, aux);
 }
 
+/* HConeBuildPrimalXSXDirection (interface/hdsdp_conic.c:335 -> sdpDenseConeBuildPrimalXSXDirection hdsdp_conic_sdp.c:2021):
+ * XSX += X * S * X with S = the dual matrix of cone k (iDualMat = 1, after refdrv_set_point) */
+void refdrv_build_xsx(refdrv *h, int k, double *X, double *XSX, int iDualMat) {
+    HConeBuildPrimalXSXDirection(h->cones[k], h->kkt, X, XSX, iDualMat);
+}
+
 int refdrv_interior_check(refdrv *h, const double *y, double tau, int *isInterior) {
     int all = 1;
     for (int k = 0; k < h->nCones; ++k) {

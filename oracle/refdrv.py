@@ -39,6 +39,9 @@ def lib():
         l.refdrv_is_kkt_sparse.argtypes = [c_void_p]
         l.refdrv_set_point.argtypes = [c_void_p, c_double_p, c_double, c_double, c_double_p]
         l.refdrv_interior_check.argtypes = [c_void_p, c_double_p, c_double, c_int_p]
+        if hasattr(l, "refdrv_build_xsx"):
+            l.refdrv_build_xsx.argtypes = [c_void_p, c_int, c_double_p, c_double_p, c_int]
+            l.refdrv_build_xsx.restype = None
         if hasattr(l, "refdrv_get_primal"):
             l.refdrv_get_primal.argtypes = [c_void_p, c_int, c_double, c_double_p, c_double_p, c_double_p, c_double_p]
             l.refdrv_get_primal.restype = None
@@ -117,6 +120,12 @@ class RefKKT:
         f = c_int(0)
         self.l.refdrv_interior_check(self.h, _dp(y), float(tau), byref(f))
         return bool(f.value)
+
+    def build_xsx(self, k, X, XSX, dual_mat=1) -> np.ndarray:
+        """HConeBuildPrimalXSXDirection: XSX += X S X (in place on a Fortran-ordered copy, returned)."""
+        X = np.asfortranarray(X, dtype=np.float64); out = np.asfortranarray(XSX, dtype=np.float64).copy(order="F")
+        self.l.refdrv_build_xsx(self.h, int(k), _dp(X), _dp(out), int(dual_mat))
+        return out
 
     def get_primal(self, k, dim, mu, y, dy) -> np.ndarray:
         """HConeGetPrimal on cone k (reference primal recovery)."""
