@@ -51,6 +51,7 @@ int hdsdpcu_init(int device) {
         if (const char *e = getenv("HDSDPCU_GEMM_VARIANT")) hd_gemm_set_variant(atoi(e));
         if (const char *e = getenv("HDSDPCU_CHOL_BLOCK")) hd_chol_set_block(atoi(e));
         if (const char *e = getenv("HDSDPCU_CHOL_LEAF")) hd_chol_set_leaf(atoi(e));
+        if (const char *e = getenv("HDSDPCU_CHOL_GRAPH")) hd_chol_set_graph(atoi(e));
     }
     g_ready = true;
     return HD_OK;
@@ -74,6 +75,7 @@ int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "chol_block") == 0) { hd_chol_set_block(value); return HD_OK; }
     if (name && strcmp(name, "chol_leaf") == 0) { hd_chol_set_leaf(value); return HD_OK; }
     if (name && strcmp(name, "trsv_version") == 0) { hd_trsv_set_version(value); return HD_OK; }
+    if (name && strcmp(name, "chol_graph") == 0) { hd_chol_set_graph(value); return HD_OK; }
     return HD_FAILED;
 }
 

@@ -542,6 +542,7 @@ void chol_destroy(DenseChol *c) {
     cudaFreeHost(c->hinfo);
     if (c->work) cudaFree(c->work);
     if (c->dfloor) { cudaFree(c->dfloor); cudaFree(c->dperturb); }
+    if (c->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t) c->graph_exec);
     free(c);
 }
 
@@ -696,8 +697,8 @@ int chol_ldl_prepare(cudaStream_t st, DenseChol *c, int nb, int rank, int nranks
 
 // Cholesky (c->ldl == false; *info = LAPACK dpotrf info) or LDL^T with unit-magnitude D (c->ldl == true; always
 // "succeeds": *info = 0, c->nperturbed / c->nnegative report the static pivots and the inertia)
-int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
-    HD_CALL(ensure_leaf_attr());
+// everything chol_factor enqueues for the factorisation proper (main + side stream); also what gets captured in a graph
+static int enqueue_factor(cudaStream_t st, DenseChol *c, int nb) {
     HD_CUDA(cudaMemsetAsync(c->dinfo, 0, sizeof(int), st));
     LdlCtx ctx{};
     if (c->ldl) {
@@ -705,15 +706,58 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
         ctx.sgn = c->sgn; ctx.dinv_base = c->Dinv; ctx.floorp = c->dfloor; ctx.nperturb = c->dperturb;
         g_ldl = &ctx;
     }
-    int nb = g_lookahead_nb;
-    if (nb < 0) nb = c->np < 24000 ? 256 : (c->np < 40000 ? 1024 : 2048);
     int rc;
     if (nb >= HD_LEAF && c->np >= 4 * nb)
         rc = potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF);
     else
         rc = potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0);
     g_ldl = nullptr;
-    HD_CALL(rc);
+    return rc;
+}
+
+static int g_use_graph = 1;
+void hd_chol_set_graph(int on) { g_use_graph = on; }
+
+int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
+    HD_CALL(ensure_leaf_attr());
+    int nb = g_lookahead_nb;
+    if (nb < 0) nb = c->np < 24000 ? 256 : (c->np < 40000 ? 1024 : 2048);
+    // Up to n = 6k the factorisation is a launch-bound chain of a few hundred small kernels on two streams whose shapes
+    // depend only on (n, block, mode): the second call with the same configuration captures it into a CUDA graph, later
+    // calls replay the graph (one launch, dependencies resolved on the device).  The first call runs eagerly so that
+    // every lazy allocation / function attribute exists before the capture.  Measured (tools/probe_block.py): -4 % at n = 1500,
+    // -3 % at 4096, +2 % at 8192 and beyond (stream priorities are not honoured inside a graph), hence the size limit.
+    const unsigned long long key = 1ull | ((unsigned long long) nb << 8) | ((unsigned long long) (c->ldl ? 1 : 0) << 1) |
+                                   ((unsigned long long) g_leaf_version << 2) | ((unsigned long long) hd_gemm_get_variant() << 4);
+    const bool graph_ok = g_use_graph && c->np <= 6144 && getenv("HDSDPCU_TRACE") == nullptr;
+    if (graph_ok && c->graph_exec && c->graph_key == key) {
+        HD_CUDA(cudaGraphLaunch((cudaGraphExec_t) c->graph_exec, st));
+        g_hd_launches += c->graph_kernels; // the kernels inside the replayed graph
+    } else if (graph_ok && c->eager_key == key) {
+        if (c->graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t) c->graph_exec); c->graph_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        HD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const long before = g_hd_launches;
+        int rc = enqueue_factor(st, c, nb);
+        c->graph_kernels = g_hd_launches - before;
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != HD_OK || ce != cudaSuccess || !graph) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            fprintf(stderr, "[hdsdpcu] graph capture of the factorisation failed (%s); running eagerly\n", cudaGetErrorString(ce));
+            g_use_graph = 0;
+            HD_CALL(enqueue_factor(st, c, nb));
+        } else {
+            cudaGraphExec_t exec = nullptr;
+            HD_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            c->graph_exec = exec; c->graph_key = key;
+            HD_CUDA(cudaGraphLaunch(exec, st));
+        }
+    } else {
+        HD_CALL(enqueue_factor(st, c, nb));
+        c->eager_key = key;
+    }
     HDK(leaf_transpose_all_kernel)<<<dim3(4, 4, c->np / HD_LEAF), dim3(32, 8), 0, st>>>(c->Dinv, c->DinvT);
     HD_CUDA(cudaGetLastError());
     HD_CUDA(cudaMemcpyAsync(c->hinfo, c->dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));

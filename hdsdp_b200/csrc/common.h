@@ -87,6 +87,8 @@ void hd_ldl_scope(DenseChol *c);
 int chol_ldl_prepare(cudaStream_t st, DenseChol *c, int nb, int rank, int nranks); // transposed inverse leaves for the L^T solve
 int hd_num_sms();
 void hd_gemm_set_variant(int v);
+int hd_gemm_get_variant();
+void hd_chol_set_graph(int on);
 void hd_chol_set_block(int nb);
 void hd_chol_set_leaf(int v);
 void hd_trsv_set_version(int v);
@@ -112,6 +114,10 @@ struct DenseChol {
     double *dfloor;  // device scalar: static-pivoting floor = 1e-13 max|diag A|
     int *dperturb;   // device: number of pivots replaced by the floor
     int nperturbed, nnegative;
+    // CUDA graph of the factorisation (launch-bound sizes), see chol_factor
+    void *graph_exec;
+    unsigned long long graph_key, eager_key;
+    long graph_kernels;
 };
 
 int chol_create(DenseChol **pc, int n);

@@ -287,6 +287,7 @@ int launch_variant(cudaStream_t st, const GemmArgs &g) {
 } // namespace
 
 void hd_gemm_set_variant(int v) { g_variant = v; }
+int hd_gemm_get_variant() { return g_variant; }
 
 int hd_num_sms() {
     if (g_num_sms == 0) {

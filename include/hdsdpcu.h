@@ -41,7 +41,8 @@ int hdsdpcu_debug_leafclk(long long *out);
  *   "chol_block"   NB of the blocked look-ahead Cholesky, used when the padded dimension is >= 4 NB
  *                  (-1 = chosen by size, the default; 0 = pure recursion)
  *   "chol_leaf"    128x128 leaf kernel: 1 = column sweep, 2 = DMMA panels (default)
- *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default) */
+ *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default)
+ *   "chol_graph"   1 (default): factorisations up to n = 6144 are replayed from a captured CUDA graph from their third call on */
 int hdsdpcu_set_option(const char *name, int value);
 
 /* ---------------------------------------------------------------------------------------------
