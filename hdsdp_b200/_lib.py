@@ -69,6 +69,7 @@ _SIGNATURES = {
     "hdsdpcu_cone_lanczosmultiply": (c_int, [c_void_p, c_int, c_double_p, c_double_p]),
     "hdsdpcu_cone_lanczossteps": (c_int, [c_void_p]),
     "hdsdpcu_cone_buildprimalxsx": (c_int, [c_void_p, c_double_p, c_double_p, c_int]),
+    "hdsdpcu_sym_extreme_eig": (c_int, [c_int, c_double_p, c_int, c_double_p, c_int_p]),
     "hdsdpcu_cone_getprimal": (c_int, [c_void_p, c_double, c_double_p, c_double_p, c_double_p, c_int_p]),
     "hdsdpcu_cone_setsinv": (c_int, [c_void_p, c_double_p]),
     "hdsdpcu_cone_setsinv_linsys": (c_int, [c_void_p, c_void_p]),

@@ -358,6 +358,10 @@ int hdsdpcu_cone_scal(void *cone, double dScal) {
 int hdsdpcu_cone_buildprimalxsx(void *cone, const double *dPrimalScalMatrix, double *dPrimalXSXBuffer, int iDualMat) {
     return cone_build_xsx((ConeCU *) cone, dPrimalScalMatrix, dPrimalXSXBuffer, iDualMat);
 }
+int hdsdpcu_sym_extreme_eig(int n, const double *X, int largest, double *eig, int *lanczosSteps) {
+    HD_CALL(ensure_ready());
+    return sym_extreme_eig(n, X, largest, eig, lanczosSteps);
+}
 int hdsdpcu_cone_getprimal(void *cone, double dBarrierMu, const double *dRowDual, const double *dRowDualStep, double *dConePrimal, int *isFeasible) {
     return cone_get_primal((ConeCU *) cone, dBarrierMu, dRowDual, dRowDualStep, dConePrimal, isFeasible);
 }

@@ -150,6 +150,7 @@ int cone_ratio_test(ConeCU *c, double dTauStep, const double *dyHost, double dAd
 int cone_lanczos_multiply(ConeCU *c, int which, const double *x, double *y);
 int cone_lanczos_steps(ConeCU *c);
 void lz_destroy(LanczosCU *l);
+int sym_extreme_eig(int n, const double *Xhost, int which, double *out, int *steps);
 
 int kkt_create(KktCU **pk, int nRow);
 void kkt_destroy(KktCU *k);

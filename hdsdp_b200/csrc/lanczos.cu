@@ -336,3 +336,56 @@ int cone_ratio_test(ConeCU *c, double dTauStep, const double *dyHost, double dAd
 }
 
 int cone_lanczos_steps(ConeCU *c) { return c->lanczos ? c->lanczos->lastSteps : 0; }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Extreme eigenvalue of a symmetric matrix (the DIMACS check of HDSDPCheckSolution, interface/hdsdp.c:852-861,
+// runs dsyevr on every primal block X -- O(n^3) on the host -- to get ONE eigenvalue: fds_syev(n, X, d, Y, 1, ...) asks for
+// index n, i.e. the LARGEST one, which the reference then records as "dMinPrimalEVal").  Here: Lanczos on the device
+// (symv + the step kernel above), Ritz values of the tridiagonal by Jacobi on the host every 10 steps, stop when the
+// residual bound |beta_k y_k| of the wanted Ritz pair is below 1e-12 ||X||.  which = 1: largest, which = 0: smallest.
+// ------------------------------------------------------------------------------------------------------------------
+int sym_extreme_eig(int n, const double *Xhost, int which, double *out, int *steps) {
+    cudaStream_t st = hd_stream();
+    if (n <= 0) return HD_FAILED;
+    if (n == 1) { *out = Xhost[0]; if (steps) *steps = 0; return HD_OK; }
+    const int maxit = n < 300 ? n : 300;
+    const int nH = maxit + 1;
+    double *X = nullptr, *V = nullptr, *H = nullptr, *v = nullptr, *w = nullptr, *scal = nullptr;
+    HD_CUDA(cudaMalloc(&X, sizeof(double) * (size_t) n * n));
+    HD_CUDA(cudaMalloc(&V, sizeof(double) * (size_t) n * (maxit + 1)));
+    HD_CUDA(cudaMalloc(&H, sizeof(double) * (size_t) nH * nH));
+    HD_CUDA(cudaMalloc(&v, sizeof(double) * n)); HD_CUDA(cudaMalloc(&w, sizeof(double) * n)); HD_CUDA(cudaMalloc(&scal, sizeof(double) * 8));
+    HD_CUDA(cudaMemcpyAsync(X, Xhost, sizeof(double) * (size_t) n * n, cudaMemcpyHostToDevice, st));
+    HD_CUDA(cudaMemsetAsync(H, 0, sizeof(double) * (size_t) nH * nH, st));
+    std::vector<double> hv;
+    start_vector(n, 1.0, hv);
+    HD_CUDA(cudaMemcpyAsync(w, hv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    HDK(lz_start_kernel)<<<1, LZ_THREADS, 0, st>>>(n, nullptr, w, v, V);
+    std::vector<double> hH((size_t) nH * nH), hs(2);
+    int rc = HD_OK, k = 0;
+    double best = 0.0, scale = 0.0;
+    for (k = 0; k < maxit; ++k) {
+        HDK(neg_symv_kernel)<<<(n + 127) / 128, 1024, 0, st>>>(X, n, n, v, w);             // w = -X v_k
+        HDK(lz_step_kernel)<<<1, LZ_THREADS, 0, st>>>(n, k, V, n, w, v, H, nH, scal);
+        if ((k + 1) % 10 != 0 && k + 1 != maxit) continue;
+        if (cudaMemcpyAsync(hH.data(), H, sizeof(double) * (size_t) nH * nH, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { rc = HD_FAILED; break; }
+        const int kp = k + 1;
+        std::vector<double> T((size_t) kp * kp), ev, Q;
+        for (int i = 0; i < kp; ++i)
+            for (int j = 0; j < kp; ++j) T[(size_t) i * kp + j] = 0.5 * (hH[(size_t) nH * i + j] + hH[(size_t) nH * j + i]);
+        jacobi_eig(kp, T, ev, Q);
+        // operator is -X: lambda_max(X) = -theta_min, lambda_min(X) = -theta_max
+        const int idx = which ? 0 : kp - 1;
+        best = -ev[idx];
+        scale = fmax(fabs(ev[0]), fabs(ev[kp - 1]));
+        const double beta = hH[(size_t) nH * k + kp];                                       // H(k+1, k)
+        const double resid = fabs(beta * Q[(size_t) idx * kp + k]);
+        if (resid <= 1e-12 * fmax(scale, 1e-300) || beta == 0.0) { ++k; break; }
+    }
+    if (steps) *steps = k;
+    *out = best;
+    cudaFree(X); cudaFree(V); cudaFree(H); cudaFree(v); cudaFree(w); cudaFree(scal);
+    return rc;
+}

@@ -132,6 +132,10 @@ int  hdsdpcu_cone_lanczossteps(void *cone);
 /* Primal recovery.  conePRecover = sdpDenseConeGetPrimal (hdsdp_conic_sdp.c:2395-2446): with S = C - A'y
  * (checked for positive definiteness in BUFFER_DUALCHECK) and dS = A'dy, dConePrimal (n x n, column-major, full symmetric)
  * = mu (S^-1 + S^-1 dS S^-1).  *isFeasible = 0 reproduces the reference's "Recovery step is infeasible" (nothing written). */
+/* Extreme eigenvalue of a symmetric n x n host matrix by Lanczos on the device (largest != 0: lambda_max, else lambda_min),
+ * to 1e-12 ||X||.  Replaces the dsyevr call of the DIMACS check (HDSDPCheckSolution, interface/hdsdp.c:852-861:
+ * fds_syev(n, X, d, Y, 1, ...) returns the LARGEST eigenvalue of the primal block). */
+int  hdsdpcu_sym_extreme_eig(int n, const double *X, int largest, double *eig, int *lanczosSteps);
 /* coneBuildPrimalDirection = sdpDenseConeBuildPrimalXSXDirection (hdsdp_conic_sdp.c:2021, fds_trimultiply dense_opts.c:102), used by
  * the PSDP primal refinement: dPrimalXSXBuffer += X S X, S = BUFFER_DUALVAR (iDualMat != 0) or BUFFER_DUALSTEP; host n x n matrices. */
 int  hdsdpcu_cone_buildprimalxsx(void *cone, const double *dPrimalScalMatrix, double *dPrimalXSXBuffer, int iDualMat);
