@@ -332,7 +332,7 @@ def run_ours(args):
                        "parallelism": (f"M 1-D block-cyclic (nb={args.dist_block}) over {world} GPUs, peer-memory panel exchange; S-side work replicated" if world > 1 else "single GPU"),
                        "step": "S update + Cholesky(S) + S^-1 + Schur M + regularize + Cholesky(M) + 2 solves", "setup_s": setup_s},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": 21.28e9,
+                         "traffic": 20.93e9,
                          "traffic_note": "dram__bytes_read+write of ONE representative dgemm_nt launch (32768^2 lower, K=2048: 2.2e12 of the "
                                          "factorisation's 4.17e13 flop), ncu --set full, profiles/README.md; algorithmic 9.1e9 B for that launch",
                          "kernel": "dgemm_nt_kernel (DMMA) inside Cholesky(M): m^3/3 flop per factorisation" + (f", split over {world} GPUs (achieved is per GPU)" if world > 1 else ""),
