@@ -71,6 +71,10 @@ _SIGNATURES = {
     "hdsdpcu_cone_buildprimalxsx": (c_int, [c_void_p, c_double_p, c_double_p, c_int]),
     "hdsdpcu_sym_extreme_eig": (c_int, [c_int, c_double_p, c_int, c_double_p, c_int_p]),
     "hdsdpcu_cone_getprimal": (c_int, [c_void_p, c_double, c_double_p, c_double_p, c_double_p, c_int_p]),
+    "hdsdpcu_cone_xdots": (c_int, [c_void_p, c_double_p, c_double_p]),
+    "hdsdpcu_cone_getdual": (c_int, [c_void_p, c_double_p]),
+    "hdsdpcu_timer_start": (c_int, []),
+    "hdsdpcu_timer_stop": (c_int, [c_double_p]),
     "hdsdpcu_cone_setsinv": (c_int, [c_void_p, c_double_p]),
     "hdsdpcu_cone_setsinv_linsys": (c_int, [c_void_p, c_void_p]),
     "hdsdpcu_cone_getbuffer": (c_int, [c_void_p, c_int, c_double_p]),

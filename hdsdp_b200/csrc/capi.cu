@@ -70,6 +70,25 @@ long hdsdpcu_launch_count(int reset) {
     return v;
 }
 
+// Device-time bracket for the host shims (integration/): two events on the library stream around one call of the hot path.
+// The side stream of the factorisations forks from and joins the library stream, so the bracket covers it.
+static cudaEvent_t g_tm_ev[2] = {nullptr, nullptr};
+int hdsdpcu_timer_start(void) {
+    HD_CALL(ensure_ready());
+    if (!g_tm_ev[0]) { HD_CUDA(cudaEventCreate(&g_tm_ev[0])); HD_CUDA(cudaEventCreate(&g_tm_ev[1])); }
+    HD_CUDA(cudaEventRecord(g_tm_ev[0], g_stream));
+    return HD_OK;
+}
+int hdsdpcu_timer_stop(double *ms) {
+    if (!g_tm_ev[0]) return HD_FAILED;
+    HD_CUDA(cudaEventRecord(g_tm_ev[1], g_stream));
+    HD_CUDA(cudaEventSynchronize(g_tm_ev[1]));
+    float f = 0.f;
+    HD_CUDA(cudaEventElapsedTime(&f, g_tm_ev[0], g_tm_ev[1]));
+    if (ms) *ms = (double) f;
+    return HD_OK;
+}
+
 int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "gemm_variant") == 0) { hd_gemm_set_variant(value); return HD_OK; }
     if (name && strcmp(name, "chol_block") == 0) { hd_chol_set_block(value); return HD_OK; }
@@ -361,6 +380,15 @@ int hdsdpcu_cone_buildprimalxsx(void *cone, const double *dPrimalScalMatrix, dou
 int hdsdpcu_sym_extreme_eig(int n, const double *X, int largest, double *eig, int *lanczosSteps) {
     HD_CALL(ensure_ready());
     return sym_extreme_eig(n, X, largest, eig, lanczosSteps);
+}
+int hdsdpcu_cone_xdots(void *cone, const double *dConePrimal, double *xDotS) {
+    return cone_xdots((ConeCU *) cone, dConePrimal, xDotS);
+}
+int hdsdpcu_cone_getdual(void *cone, double *dConeDual) {
+    // coneDRecover (sdpDenseConeGetDual, hdsdp_conic_sdp.c:2497-2508): the dual matrix, full symmetric
+    ConeCU *c = (ConeCU *) cone;
+    HD_CALL(hd_symmetrize_lower(g_stream, c->d_buf[BUF_DUALVAR], c->np, c->np));
+    return hdsdpcu_cone_getbuffer(cone, BUF_DUALVAR, dConeDual);
 }
 int hdsdpcu_cone_getprimal(void *cone, double dBarrierMu, const double *dRowDual, const double *dRowDualStep, double *dConePrimal, int *isFeasible) {
     return cone_get_primal((ConeCU *) cone, dBarrierMu, dRowDual, dRowDualStep, dConePrimal, isFeasible);

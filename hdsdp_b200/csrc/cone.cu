@@ -919,6 +919,43 @@ int cone_build_xsx(ConeCU *c, const double *Xhost, double *XSXhost, int iDualMat
     return HD_OK;
 }
 
+// coneXDotS (reference sdpDenseConeXDotS hdsdp_conic_sdp.c:2549-2558 -> fds_dot_fds linalg/dense_opts.c:134-156):
+// <S, X> from the LOWER triangles of both, 2 * (sum_{i>j} S_ij X_ij + 0.5 sum_i S_ii X_ii); X is a host n x n matrix.
+__global__ void lower_dot_kernel(const double *__restrict__ S, const double *__restrict__ X, long ld, int n, double *out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    const long total = (long) n * n;
+    for (long idx = (long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long) gridDim.x * blockDim.x) {
+        const int i = (int) (idx % n), j = (int) (idx / n);
+        if (i < j) continue;
+        const double v = S[(long) j * ld + i] * X[(long) j * ld + i];
+        s += (i == j) ? 0.5 * v : v;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, 2.0 * red[0]);
+}
+
+int cone_xdots(ConeCU *c, const double *Xhost, double *out) {
+    cudaStream_t st = hd_stream();
+    const int n = c->n, np = c->np;
+    HD_CALL(ensure_UB(c));
+    HD_CUDA(cudaMemcpy2DAsync(c->d_U, (size_t) np * 8, Xhost, (size_t) n * 8, (size_t) n * 8, n, cudaMemcpyHostToDevice, st));
+    HD_CUDA(cudaMemsetAsync(c->d_scal + 6, 0, sizeof(double), st));
+    long blocks = ((long) n * n + 255) / 256;
+    if (blocks > 4 * hd_num_sms()) blocks = 4 * hd_num_sms();
+    HDK(lower_dot_kernel)<<<(unsigned) blocks, 256, 0, st>>>(c->d_buf[BUF_DUALVAR], c->d_U, np, n, c->d_scal + 6);
+    HD_CUDA(cudaGetLastError());
+    HD_CUDA(cudaMemcpyAsync(c->h_scal + 6, c->d_scal + 6, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HD_CUDA(cudaStreamSynchronize(st));
+    *out = c->h_scal[6];
+    return HD_OK;
+}
+
 // U_i = A_i Sinv for ALL dense rows in one GEMM: rows (i, c) of the vec layout are an affine index, K = k
 static int dd_compute_U(ConeCU *c, cudaStream_t st) {
     GemmArgs g{};

@@ -144,6 +144,7 @@ int cone_update_buffer(ConeCU *c, double cCoef, double aScal, const double *aCoe
 int cone_factorize(ConeCU *c, int which, int *isPsd);
 int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT);
 int cone_build_xsx(ConeCU *c, const double *Xhost, double *XSXhost, int iDualMat);
+int cone_xdots(ConeCU *c, const double *Xhost, double *out);
 int cone_get_primal(ConeCU *c, double mu, const double *yHost, const double *dyHost, double *Xhost, int *isFeasible);
 // lanczos.cu
 int cone_ratio_test(ConeCU *c, double dTauStep, const double *dyHost, double dAdaRatio, int which, double *maxStep);

@@ -29,6 +29,10 @@ int hdsdpcu_sync(void);
 const char *hdsdpcu_version(void);
 /* count of kernel launches issued by this library since the last reset (bench.py "gpu_launches") */
 long hdsdpcu_launch_count(int reset);
+/* device-time bracket around calls of this library (two CUDA events on the library stream; stop synchronises and returns the
+ * elapsed milliseconds).  Used by the host shims of integration/ to report how much of the hot path's wall time is device time. */
+int hdsdpcu_timer_start(void);
+int hdsdpcu_timer_stop(double *ms);
 /* device-to-device copy on the library stream (bench plumbing for HBM-resident inputs) */
 int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes);
 /* debug: clock64() stamps of the phases of the last leaf factorisation (40 values, tools/leafclk.py) */
@@ -141,6 +145,10 @@ int  hdsdpcu_sym_extreme_eig(int n, const double *X, int largest, double *eig, i
 int  hdsdpcu_cone_buildprimalxsx(void *cone, const double *dPrimalScalMatrix, double *dPrimalXSXBuffer, int iDualMat);
 int  hdsdpcu_cone_getprimal(void *cone, double dBarrierMu, const double *dRowDual, const double *dRowDualStep,
                             double *dConePrimal, int *isFeasible);
+/* coneXDotS = sdpDenseConeXDotS (hdsdp_conic_sdp.c:2549, fds_dot_fds dense_opts.c:134): <S, X> over the lower triangles, X host n x n.
+ * coneDRecover = sdpDenseConeGetDual (:2497): the dual matrix S (BUFFER_DUALVAR), full symmetric, to a host n x n matrix. */
+int  hdsdpcu_cone_xdots(void *cone, const double *dConePrimal, double *xDotS);
+int  hdsdpcu_cone_getdual(void *cone, double *dConeDual);
 /* Hand the cone an S^-1 computed elsewhere (used by the integration shim, whose S factor is owned by the
  * reference's hdsdp_linsys_fp): from a host n x n matrix, or device-to-device from a hdsdpcu_linsys handle
  * (HFpLinsysInvert, linalg/hdsdp_linsolver.c:2120, without the host round trip).  Valid until the next update. */

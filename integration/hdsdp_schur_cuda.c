@@ -13,8 +13,9 @@
  *   HKKTBuildUpExtraCone-> bound cone: the O(m) host arithmetic of sBoundConeGetKKT
  *                          (interface/hdsdp_conic_bound.c:201-249) is kept, its writes go through hdsdpcu_kkt_addhost
  *   HKKTRegularize / HKKTFactorize / HKKTSolve / HKKTExport -> hdsdpcu_kkt_*
- * S^-1 comes from the cone's own dual factor: device-to-device when that factor is the CUDA linsys back-end
- * (integration/hdsdp_linsys_cuda.c), otherwise HFpLinsysInvert on the host followed by one upload.
+ * The SDP cones themselves live on the device (integration/hdsdp_conic_cuda.c binds the cone vtable), so S^-1 is computed
+ * from the device-resident Cholesky factor of S inside hdsdpcu_cone_buildschur: no dual matrix, factor or inverse ever crosses
+ * PCIe.  A cone that was not bound by the cone hook is an error (there is no host path for S).
  *
  * This is original code written against the reference's headers; it is not derived from hdsdp_schur.c's body.
  */
@@ -28,27 +29,43 @@
 #include "interface/hdsdp_conic.h"
 #include "interface/def_hdsdp_user_data.h"
 #include "hdsdpcu.h"
-
-int hdsdpcu_linsys_is_cuda(hdsdp_linsys_fp *lin); /* integration/hdsdp_linsys_cuda.c */
+#include "hdsdpcu_shim.h"
 
 typedef struct {
     void *dkkt;              /* hdsdpcu kkt handle */
     int nCones;
-    void **dcone;            /* per cone: hdsdpcu cone handle (SDP), lp handle (LP) or NULL */
-    double *objScal;         /* per cone: scale applied to the objective by HConeScalByConstant (detected lazily) */
-    int *scaled;
-    double *hostInv;         /* maxConeDim^2 staging for host-side inverses */
+    void **dcone;            /* per cone: hdsdpcu cone handle (SDP, owned by the cone hook), lp handle (LP, owned here) or NULL */
     double *vecA, *vecB, *vecC, *vecD;
 } kkt_cuda;
 
-/* one side table keyed by the hdsdp_kkt pointer (the struct layout must stay the reference's) */
-#define MAX_KKT 16
-static hdsdp_kkt *g_keys[MAX_KKT];
-static kkt_cuda *g_vals[MAX_KKT];
+/* side table keyed by the hdsdp_kkt pointer (the struct layout must stay the reference's); grows on demand */
+static hdsdp_kkt **g_keys = NULL;
+static kkt_cuda **g_vals = NULL;
+static int g_cap = 0;
 
 static kkt_cuda *lookup(hdsdp_kkt *k) {
-    for (int i = 0; i < MAX_KKT; ++i) if (g_keys[i] == k) return g_vals[i];
+    for (int i = 0; i < g_cap; ++i) if (g_keys[i] == k) return g_vals[i];
     return NULL;
+}
+
+static int table_insert(hdsdp_kkt *k, kkt_cuda *v) {
+    for (int i = 0; i < g_cap; ++i) if (!g_keys[i]) { g_keys[i] = k; g_vals[i] = v; return 0; }
+    int ncap = g_cap ? 2 * g_cap : 8;
+    hdsdp_kkt **nk = (hdsdp_kkt **) realloc(g_keys, sizeof(hdsdp_kkt *) * ncap);
+    if ( !nk ) return 1;
+    g_keys = nk;
+    kkt_cuda **nv = (kkt_cuda **) realloc(g_vals, sizeof(kkt_cuda *) * ncap);
+    if ( !nv ) return 1;
+    g_vals = nv;
+    for (int i = g_cap; i < ncap; ++i) { g_keys[i] = NULL; g_vals[i] = NULL; }
+    g_keys[g_cap] = k; g_vals[g_cap] = v;
+    g_cap = ncap;
+    return 0;
+}
+
+void *hdsdpcu_shim_kkt_handle(void *hkkt) {
+    kkt_cuda *kc = lookup((hdsdp_kkt *) hkkt);
+    return kc ? kc->dkkt : NULL;
 }
 
 static void refresh_host_vectors(hdsdp_kkt *HKKT, kkt_cuda *kc, int typeKKT) {
@@ -91,21 +108,26 @@ extern hdsdp_retcode HKKTInit( hdsdp_kkt *HKKT, int nRow, int nCones, hdsdp_cone
     HKKT->dPrimalX = NULL;
 
     kkt_cuda *kc = (kkt_cuda *) calloc(1, sizeof(kkt_cuda));
+    if ( !kc ) return HDSDP_RETCODE_MEMORY;
     kc->nCones = nCones;
     kc->dcone = (void **) calloc(nCones > 0 ? nCones : 1, sizeof(void *));
-    kc->objScal = (double *) calloc(nCones > 0 ? nCones : 1, sizeof(double));
-    kc->scaled = (int *) calloc(nCones > 0 ? nCones : 1, sizeof(int));
-    kc->hostInv = (double *) calloc(nsq > 0 ? nsq : 1, sizeof(double));
     kc->vecA = (double *) calloc(nRow, sizeof(double)); kc->vecB = (double *) calloc(nRow, sizeof(double));
     kc->vecC = (double *) calloc(nRow, sizeof(double)); kc->vecD = (double *) calloc(nRow, sizeof(double));
-    if ( hdsdpcu_kkt_create(&kc->dkkt, nRow) != 0 ) return HDSDP_RETCODE_FAILED;
+    if ( !kc->dcone || !kc->vecA || !kc->vecB || !kc->vecC || !kc->vecD || table_insert(HKKT, kc) != 0 ) {
+        free(kc->dcone); free(kc->vecA); free(kc->vecB); free(kc->vecC); free(kc->vecD); free(kc);
+        return HDSDP_RETCODE_MEMORY;
+    }
+    int drc = hdsdpcu_kkt_create(&kc->dkkt, nRow);
+    if ( drc != 0 ) return drc == 2 ? HDSDP_RETCODE_MEMORY : HDSDP_RETCODE_FAILED;
     for ( int iCone = 0; iCone < nCones; ++iCone ) {
         hdsdp_cone *c = cones[iCone];
         user_data *u = (user_data *) c->usrData;
         if ( c->cone == HDSDP_CONETYPE_DENSE_SDP || c->cone == HDSDP_CONETYPE_SPARSE_SDP ) {
-            if ( hdsdpcu_cone_create(&kc->dcone[iCone], nRow, u->nConicCol, u->coneMatBeg, u->coneMatIdx, u->coneMatElem) != 0 )
+            kc->dcone[iCone] = hdsdpcu_shim_cone_handle(c);   /* created by the cone hook in coneProcData */
+            if ( !kc->dcone[iCone] ) {
+                printf("[hdsdpcu] SDP cone %d has no device image (cone hook not linked?); there is no host path for S\n", iCone);
                 return HDSDP_RETCODE_FAILED;
-            /* every SDP cone is registered so that cone index == position (LP slots get a NULL image) */
+            }
         } else if ( c->cone == HDSDP_CONETYPE_LP ) {
             if ( hdsdpcu_lp_create(&kc->dcone[iCone], nRow, u->nConicCol, u->coneMatBeg, u->coneMatIdx, u->coneMatElem) != 0 )
                 return HDSDP_RETCODE_FAILED;
@@ -114,65 +136,33 @@ extern hdsdp_retcode HKKTInit( hdsdp_kkt *HKKT, int nRow, int nCones, hdsdp_cone
             return HDSDP_RETCODE_FAILED;
         }
     }
-    for ( int i = 0; i < MAX_KKT; ++i ) if ( !g_keys[i] ) { g_keys[i] = HKKT; g_vals[i] = kc; break; }
-    printf("    Using dense Schur complement on the GPU (libhdsdp_cuda)\n");
+    printf("    Using dense Schur complement on the GPU (libhdsdp_cuda); SDP cones are device resident\n");
     return HDSDP_RETCODE_OK;
 }
 
-/* ||C||_F of user column 0, to detect the objective scaling applied after the image was created */
-static double raw_obj_fro(user_data *u) {
-    int n = u->nConicCol; double s = 0.0;
-    for ( int e = u->coneMatBeg[0]; e < u->coneMatBeg[1]; ++e ) {
-        int p = u->coneMatIdx[e], col = 0; long start = 0;
-        while ( col < n - 1 && start + (n - col) <= p ) { start += n - col; col++; }
-        int row = (int) (p - start) + col;
-        double v = u->coneMatElem[e];
-        s += ( row == col ) ? v * v : 2.0 * v * v;
-    }
-    return sqrt(s);
-}
-
 static hdsdp_retcode build_sdp_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, int iCone, int typeKKT ) {
-    hdsdp_cone *c = HKKT->cones[iCone];
-    void *dc = kc->dcone[iCone];
-    double rd; int n; hdsdp_linsys_fp *factor;
-    if ( c->cone == HDSDP_CONETYPE_DENSE_SDP ) {
-        hdsdp_cone_sdp_dense *d = (hdsdp_cone_sdp_dense *) c->coneData; rd = d->dualResidual; n = d->nCol; factor = d->dualFactor;
-    } else {
-        hdsdp_cone_sdp_sparse *d = (hdsdp_cone_sdp_sparse *) c->coneData; rd = d->dualResidual; n = d->nCol; factor = d->dualFactor;
-    }
-    hdsdpcu_cone_setstart(dc, rd);
-    if ( typeKKT == KKT_TYPE_HOMOGENEOUS && !kc->scaled[iCone] ) {
-        /* HConeScalByConstant (hdsdp.c:315) scaled the reference's copy of C after our image was made */
-        double raw = raw_obj_fro((user_data *) c->usrData), cur = HConeGetObjNorm(c, FRO_NORM);
-        if ( raw > 0.0 && cur > 0.0 && fabs(cur / raw - 1.0) > 1e-14 ) hdsdpcu_cone_scal(dc, cur / raw);
-        kc->scaled[iCone] = 1;
-    }
-    if ( typeKKT != KKT_TYPE_PRIMAL ) {
-        if ( hdsdpcu_linsys_is_cuda(factor) ) {
-            if ( hdsdpcu_cone_setsinv_linsys(dc, factor->chol) != 0 ) return HDSDP_RETCODE_FAILED;
-        } else {
-            HFpLinsysInvert(factor, kc->hostInv, HKKT->kktBuffer);
-            if ( hdsdpcu_cone_setsinv(dc, kc->hostInv) != 0 ) return HDSDP_RETCODE_FAILED;
-        }
-    }
-    (void) n;
-    return (hdsdp_retcode) hdsdpcu_cone_buildschur(dc, iCone, kc->dkkt, typeKKT);
+    /* S^-1 = inverse of the device-resident dual factor (hdsdp_conic_sdp.c:1755 HFpLinsysInvert), computed inside
+       hdsdpcu_cone_buildschur and cached until S is factorised again (the corrector builds of one iteration reuse it) */
+    (void) HKKT;
+    return (hdsdp_retcode) hdsdpcu_cone_buildschur(kc->dcone[iCone], iCone, kc->dkkt, typeKKT);
 }
 
 /* LP cone: the O(nnz) slack inversion stays on the host (hdsdp_conic_lp.c:262-271); M += A D^2 A' on the device */
 static hdsdp_retcode build_lp_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, int iCone, int typeKKT ) {
     hdsdp_cone_lp *lp = (hdsdp_cone_lp *) HKKT->cones[iCone]->coneData;
+    shim_prof_host_begin();
     if ( typeKKT == KKT_TYPE_PRIMAL ) {
         if ( !HKKT->dPrimalX || !HKKT->dPrimalX[iCone] ) return HDSDP_RETCODE_FAILED;
         for ( int i = 0; i < lp->nCol; ++i ) lp->colDualInverse[i] = HKKT->dPrimalX[iCone][i];
     } else {
         for ( int i = 0; i < lp->nCol; ++i ) lp->colDualInverse[i] = 1.0 / lp->colDual[i];
     }
+    shim_prof_host_end(SHIM_CAT_SCHUR);
     if ( hdsdpcu_kkt_buildupextra_lp(kc->dkkt, kc->dcone[iCone], lp->colDualInverse, lp->dualResidual, typeKKT) != 0 )
         return HDSDP_RETCODE_FAILED;
     if ( typeKKT == KKT_TYPE_HOMOGENEOUS ) { /* hdsdp_conic_lp.c:316-327: O(nnz) host arithmetic, added through addhost */
         double add[4] = {0, 0, 0, 0};
+        shim_prof_host_begin();
         memset(kc->vecC, 0, sizeof(double) * HKKT->nRow);
         for ( int i = 0; i < lp->nCol; ++i ) {
             double cs = lp->colObj[i] * lp->colDualInverse[i];
@@ -181,6 +171,7 @@ static hdsdp_retcode build_lp_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, int iCone, in
         }
         for ( int r = 0; r < lp->nRow; ++r )
             for ( int e = lp->rowMatBeg[r]; e < lp->rowMatBeg[r + 1]; ++e ) kc->vecC[r] += lp->rowMatElem[e] * lp->colBuffer[lp->rowMatIdx[e]];
+        shim_prof_host_end(SHIM_CAT_SCHUR);
         if ( hdsdpcu_kkt_addhost(kc->dkkt, NULL, NULL, NULL, kc->vecC, add) != 0 ) return HDSDP_RETCODE_FAILED;
     }
     return HDSDP_RETCODE_OK;
@@ -193,6 +184,7 @@ static hdsdp_retcode build_bound_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, hdsdp_cone
     int m = HKKT->nRow;
     double add[4] = {0, 0, 0, 0};
     int hsd = ( typeKKT == KKT_TYPE_HOMOGENEOUS );
+    shim_prof_host_begin();
     for ( int i = 0; i < b->nRow; ++i ) {
         b->dualLowerInverse[i] = 1.0 / b->dualLower[i];
         b->dualUpperInverse[i] = 1.0 / b->dualUpper[i];
@@ -207,6 +199,7 @@ static hdsdp_retcode build_bound_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, hdsdp_cone
             add[0] += b->dBoundUp * b->dBoundUp * ui * ui + b->dBoundLow * b->dBoundLow * li * li;
         }
     }
+    shim_prof_host_end(SHIM_CAT_SCHUR);
     int rc = hdsdpcu_kkt_addhost(kc->dkkt, typeKKT == KKT_TYPE_CORRECTOR ? NULL : kc->vecB, kc->vecA, NULL,
                                  hsd ? kc->vecC : NULL, hsd ? add : NULL);
     return rc == 0 ? HDSDP_RETCODE_OK : HDSDP_RETCODE_FAILED;
@@ -225,26 +218,31 @@ static hdsdp_retcode build_one( hdsdp_kkt *HKKT, kkt_cuda *kc, hdsdp_cone *cone,
 extern hdsdp_retcode HKKTBuildUp( hdsdp_kkt *HKKT, int typeKKT ) {
     kkt_cuda *kc = lookup(HKKT);
     if ( !kc ) return HDSDP_RETCODE_FAILED;
-    if ( hdsdpcu_kkt_clean(kc->dkkt, typeKKT) != 0 ) return HDSDP_RETCODE_FAILED;
-    for ( int iCone = 0; iCone < HKKT->nCones; ++iCone ) {
-        hdsdp_retcode rc = build_one(HKKT, kc, HKKT->cones[iCone], iCone, typeKKT);
-        if ( rc != HDSDP_RETCODE_OK ) return rc;
-    }
-    refresh_host_vectors(HKKT, kc, typeKKT);
-    return HDSDP_RETCODE_OK;
+    hdsdp_retcode rc = HDSDP_RETCODE_OK;
+    shim_prof_begin(SHIM_CAT_SCHUR);
+    if ( hdsdpcu_kkt_clean(kc->dkkt, typeKKT) != 0 ) rc = HDSDP_RETCODE_FAILED;
+    for ( int iCone = 0; iCone < HKKT->nCones && rc == HDSDP_RETCODE_OK; ++iCone )
+        rc = build_one(HKKT, kc, HKKT->cones[iCone], iCone, typeKKT);
+    if ( rc == HDSDP_RETCODE_OK ) refresh_host_vectors(HKKT, kc, typeKKT);
+    shim_prof_end(SHIM_CAT_SCHUR);
+    return rc;
 }
 
 extern hdsdp_retcode HKKTBuildUpExtraCone( hdsdp_kkt *HKKT, hdsdp_cone *cone, int typeKKT ) {
     kkt_cuda *kc = lookup(HKKT);
     if ( !kc ) return HDSDP_RETCODE_FAILED;
+    shim_prof_begin(SHIM_CAT_SCHUR);
     hdsdp_retcode rc = build_one(HKKT, kc, cone, cone->iCone, typeKKT);
-    if ( rc != HDSDP_RETCODE_OK ) return rc;
-    refresh_host_vectors(HKKT, kc, typeKKT);
-    return HDSDP_RETCODE_OK;
+    if ( rc == HDSDP_RETCODE_OK ) refresh_host_vectors(HKKT, kc, typeKKT);
+    shim_prof_end(SHIM_CAT_SCHUR);
+    return rc;
 }
 
 extern hdsdp_retcode HKKTBuildUpFixed( hdsdp_kkt *HKKT, int typeKKT, int kktStrategy ) {
-    (void) kktStrategy; /* M2..M5 are algebraically identical; the GPU build has one formula per class pair */
+    /* M2..M5 are algebraically identical; the GPU build has ONE formula per class pair, so the reference's own
+       M3-vs-M4 cross-check (HUtilKKTCheck, hdsdp_utils.c:536-707) compares the device result with itself through this
+       hook -- the cross-formula check lives in tests/test_cpu_oracle.py and tests/test_gpu_schur.py instead */
+    (void) kktStrategy;
     return HKKTBuildUp(HKKT, typeKKT);
 }
 
@@ -262,18 +260,27 @@ extern void HKKTExport( hdsdp_kkt *HKKT, double *dKKTASinvVec, double *dKKTASinv
 extern hdsdp_retcode HKKTFactorize( hdsdp_kkt *HKKT ) {
     kkt_cuda *kc = lookup(HKKT);
     if ( !kc ) return HDSDP_RETCODE_FAILED;
-    return hdsdpcu_kkt_factorize(kc->dkkt) == 0 ? HDSDP_RETCODE_OK : HDSDP_RETCODE_FAILED;
+    shim_prof_begin(SHIM_CAT_FACTOR);
+    int rc = hdsdpcu_kkt_factorize(kc->dkkt);
+    shim_prof_end(SHIM_CAT_FACTOR);
+    return rc == 0 ? HDSDP_RETCODE_OK : HDSDP_RETCODE_FAILED;
 }
 
 extern hdsdp_retcode HKKTSolve( hdsdp_kkt *HKKT, double *dRhsVec, double *dLhsVec ) {
     kkt_cuda *kc = lookup(HKKT);
     if ( !kc ) return HDSDP_RETCODE_FAILED;
-    return hdsdpcu_kkt_solve(kc->dkkt, dRhsVec, dLhsVec) == 0 ? HDSDP_RETCODE_OK : HDSDP_RETCODE_FAILED;
+    shim_prof_begin(SHIM_CAT_SOLVE);
+    int rc = hdsdpcu_kkt_solve(kc->dkkt, dRhsVec, dLhsVec);
+    shim_prof_end(SHIM_CAT_SOLVE);
+    return rc == 0 ? HDSDP_RETCODE_OK : HDSDP_RETCODE_FAILED;
 }
 
 extern void HKKTRegularize( hdsdp_kkt *HKKT, double dKKTReg ) {
     kkt_cuda *kc = lookup(HKKT);
-    if ( kc ) hdsdpcu_kkt_regularize(kc->dkkt, dKKTReg);
+    if ( !kc ) return;
+    shim_prof_begin(SHIM_CAT_SCHUR);
+    hdsdpcu_kkt_regularize(kc->dkkt, dKKTReg);
+    shim_prof_end(SHIM_CAT_SCHUR);
 }
 
 extern void HKKTRegisterPSDP( hdsdp_kkt *HKKT, double **dPrimalX ) {
@@ -288,13 +295,14 @@ extern void HKKTClear( hdsdp_kkt *HKKT ) {
     if ( kc ) {
         for ( int i = 0; i < kc->nCones; ++i ) {
             if ( !kc->dcone[i] ) continue;
+            /* SDP cone images belong to the cone hook (destroyed by coneDestroyData) */
             if ( HKKT->cones && HKKT->cones[i] && HKKT->cones[i]->cone == HDSDP_CONETYPE_LP ) hdsdpcu_lp_destroy(&kc->dcone[i]);
-            else hdsdpcu_cone_destroy(&kc->dcone[i]);
         }
         hdsdpcu_kkt_destroy(&kc->dkkt);
-        free(kc->dcone); free(kc->objScal); free(kc->scaled); free(kc->hostInv);
+        free(kc->dcone);
         free(kc->vecA); free(kc->vecB); free(kc->vecC); free(kc->vecD); free(kc);
-        for ( int i = 0; i < MAX_KKT; ++i ) if ( g_keys[i] == HKKT ) { g_keys[i] = NULL; g_vals[i] = NULL; }
+        for ( int i = 0; i < g_cap; ++i ) if ( g_keys[i] == HKKT ) { g_keys[i] = NULL; g_vals[i] = NULL; }
+        shim_prof_report();
     }
     free(HKKT->dASinvVec); free(HKKT->dASinvCSinvVec); free(HKKT->dASinvRdSinvVec);
     free(HKKT->invBuffer); free(HKKT->kktBuffer); free(HKKT->kktBuffer2);

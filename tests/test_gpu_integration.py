@@ -63,3 +63,36 @@ def test_full_solve_matches_cpu_reference(name):
     it_tol = 3 if name == "gpp100" else 1
     assert abs(res["iterations"] - ref_it) <= it_tol, f"iterations {res['iterations']} vs CPU reference {ref_it}"
     assert max(res["dimacs"]) <= 1e-2     # the reference's own acceptance gate (interface/hdsdp.c:905-922)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sizes at which the multi-leaf kernels run inside an IPM solve (n, m > 128: recursion, look-ahead, DMMA GEMM, multi-block
+# triangular solves, device Lanczos), against the CPU reference run LIVE on the same box (oracle/_ref, all host threads):
+# BASELINE.md section 2's two mid-size problems.  Every S / S^-1 / Schur / Cholesky operation of the integrated solve runs on
+# the device through the cone hook (integration/hdsdp_conic_cuda.c) -- for max-cut the reference itself uses a sparse S + QDLDL.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("spec", ["theta:200:3000", "maxcut:1000:4"])
+def test_midsize_full_solve_matches_live_cpu_reference(spec):
+    if not os.path.exists(INTEGRATED):
+        pytest.skip("integration/_build/libhdsdp_integrated.so not built (needs /root/reference at build time)")
+    sys.path.insert(0, ROOT)
+    from tools import fullsolve
+    from oracle import refdrv
+    if not refdrv.available():
+        pytest.skip("oracle/_ref not built")
+    s = fullsolve.parse_spec(spec)
+    gpu, log, err = fullsolve.run(s, True, 1)
+    assert gpu is not None, f"integrated solve of {spec} produced no result:\n{log[-3000:]}\n{err[-3000:]}"
+    assert "SDP cones are device resident" in log
+    ref, rlog, rerr = fullsolve.run(s, False, os.cpu_count() or 1)
+    assert ref is not None, f"reference solve of {spec} produced no result:\n{rlog[-3000:]}\n{rerr[-3000:]}"
+    assert gpu["retcode"] == 0 and gpu["status"] == ref["status"], (gpu, ref)
+    assert abs(gpu["dObj"] - ref["dObj"]) <= 1e-7 * max(1.0, abs(ref["dObj"])), (gpu["dObj"], ref["dObj"])
+    ptol = 1e-7 * max(1.0, abs(ref["pObj"])) + 2.0 * abs(ref["pObj"] - ref["dObj"])
+    assert abs(gpu["pObj"] - ref["pObj"]) <= ptol, (gpu["pObj"], ref["pObj"], ptol)
+    assert abs(gpu["iterations"] - ref["iterations"]) <= 1, (gpu["iterations"], ref["iterations"])
+    assert max(gpu["dimacs"]) <= 1e-2
+    acc = fullsolve.parse_accounting(log)
+    assert acc.get("factorisations", 0) >= gpu["iterations"] - 1, acc      # one Cholesky(M) per IPM iteration, all on the device
+    print(f"{spec}: GPU {gpu['seconds']:.2f} s / {gpu['iterations']} its, CPU reference {ref['seconds']:.2f} s / {ref['iterations']} its, "
+          f"GPU share of the hot path {acc.get('gpu_share_pct')}%")

@@ -1,0 +1,126 @@
+"""Full IPM solves through the drop-in build (unmodified reference host + the three hook files of integration/), with the CPU
+reference run beside it where it is affordable.
+
+    python tools/fullsolve.py maxcut:1000:4 theta:200:3000 theta:1500:5000 maxcut:8000:6 [--no-ref NAME ...] [--out DIR]
+
+For every problem: generate it (hdsdp_b200/problem.py, deterministic seeds), solve it in a subprocess through
+integration/_build/libhdsdp_integrated.so (every S / Schur / Cholesky operation on the GPU), keep the solver's own iteration
+log and the hook accounting report ("[hdsdpcu] hot-path accounting": wall vs device time, GPU share), and -- unless the name
+is listed after --no-ref -- solve it again with oracle/_ref (the unmodified CPU reference) and compare objectives (1e-7
+relative) and iteration counts (+-1).  Writes one JSON line per problem and the raw logs to --out (default gpurun_out/).
+
+Test / measurement infrastructure: the only part of the repo besides tests/ and bench.py that runs oracle/_ref.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INTEGRATED = os.path.join(ROOT, "integration", "_build", "libhdsdp_integrated.so")
+
+HELPER = r"""
+import json, sys, time
+sys.path.insert(0, {root!r})
+from hdsdp_b200 import problem
+from oracle import refdrv
+kind, a, b = {spec!r}
+if kind == "maxcut":
+    prob = problem.gen_maxcut(a, degree=b, seed=1)
+elif kind == "theta":
+    prob = problem.gen_theta(a, b, seed=2)
+elif kind == "multiblock":
+    prob = problem.gen_multiblock(a, n1=b, n2=b + 20, ndense=max(a // 7, 1), nlp=max(a // 4, 1), seed=3)
+else:
+    raise SystemExit("unknown problem kind " + kind)
+t0 = time.time()
+res = refdrv.optimize(prob, max_iter={max_iter})
+print("RESULT " + json.dumps({{"m": prob.m, "n": [c.dim for c in prob.cones], "pObj": res["pObj"], "dObj": res["dObj"],
+                              "iterations": res["iterations"], "status": res["status"], "retcode": res["retcode"],
+                              "dimacs": list(res["dimacs"]), "seconds": res["seconds"], "wall": time.time() - t0}}))
+"""
+
+
+def parse_spec(s):
+    p = s.split(":")
+    return p[0], int(p[1]), int(p[2])
+
+
+def run(spec, integrated, threads, max_iter=0, timeout=3000):
+    env = dict(os.environ, OPENBLAS_NUM_THREADS=str(threads))
+    if integrated:
+        env["HDSDP_REFDRV_LIB"] = INTEGRATED
+    else:
+        env.pop("HDSDP_REFDRV_LIB", None)
+    code = HELPER.format(root=ROOT, spec=spec, max_iter=max_iter)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=timeout)
+    res = None
+    for ln in out.stdout.splitlines():
+        if ln.startswith("RESULT "):
+            res = json.loads(ln[7:])
+    return res, out.stdout, out.stderr
+
+
+def parse_accounting(log):
+    """The hook report printed by integration/hdsdpcu_shim.c."""
+    acc = {"stages": {}}
+    for ln in log.splitlines():
+        m = re.match(r"\s+(.+?)\s+(\d+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)%\s*$", ln)
+        if m:
+            acc["stages"][m.group(1).strip()] = {"calls": int(m.group(2)), "wall_s": float(m.group(3)), "device_s": float(m.group(4)),
+                                                 "host_s": float(m.group(5)), "gpu_pct": float(m.group(6))}
+        m = re.search(r"wall ([\d.]+) s, device ([\d.]+) s, host arithmetic ([\d.]+) s -> GPU share ([\d.]+)%", ln)
+        if m:
+            acc.update(hot_wall_s=float(m.group(1)), hot_device_s=float(m.group(2)), hot_host_s=float(m.group(3)),
+                       gpu_share_pct=float(m.group(4)))
+        m = re.search(r"(\d+) factorisations of M: ([\d.]+) s hot path per factorisation", ln)
+        if m:
+            acc.update(factorisations=int(m.group(1)), hot_s_per_iteration=float(m.group(2)))
+    return acc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("specs", nargs="+")
+    ap.add_argument("--no-ref", nargs="*", default=[])
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--max-iter", type=int, default=0)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    rc = 0
+    for s in args.specs:
+        spec = parse_spec(s)
+        tag = s.replace(":", "_")
+        t0 = time.time()
+        gpu, log, err = run(spec, True, 1, args.max_iter)
+        open(os.path.join(args.out, f"fullsolve_{tag}_gpu.log"), "w").write(log + "\n--- stderr ---\n" + err[-5000:])
+        rec = {"problem": s, "gpu": gpu, "gpu_wall_s": time.time() - t0, "accounting": parse_accounting(log)}
+        if gpu is None:
+            rec["error"] = "integrated solve produced no result"
+            rc = 1
+        elif s not in args.no_ref:
+            t1 = time.time()
+            ref, rlog, rerr = run(spec, False, args.threads, args.max_iter)
+            open(os.path.join(args.out, f"fullsolve_{tag}_ref.log"), "w").write(rlog + "\n--- stderr ---\n" + rerr[-5000:])
+            rec["ref"] = ref
+            rec["ref_wall_s"] = time.time() - t1
+            rec["ref_threads"] = args.threads
+            if ref is not None:
+                rec["dobj_rel_diff"] = abs(gpu["dObj"] - ref["dObj"]) / max(1.0, abs(ref["dObj"]))
+                rec["pobj_rel_diff"] = abs(gpu["pObj"] - ref["pObj"]) / max(1.0, abs(ref["pObj"]))
+                rec["iter_diff"] = gpu["iterations"] - ref["iterations"]
+                rec["parity_ok"] = bool(rec["dobj_rel_diff"] <= 1e-7 and abs(rec["iter_diff"]) <= 1 and gpu["status"] == ref["status"])
+                if not rec["parity_ok"]:
+                    rc = 1
+        print(json.dumps(rec), flush=True)
+        with open(os.path.join(args.out, "fullsolve.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())
