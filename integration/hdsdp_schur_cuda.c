@@ -35,6 +35,7 @@ typedef struct {
     void *dkkt;              /* hdsdpcu kkt handle */
     int nCones;
     void **dcone;            /* per cone: hdsdpcu cone handle (SDP, owned by the cone hook), lp handle (LP, owned here) or NULL */
+    int *ownsLp;             /* per cone: dcone[i] is an LP image created (and to be destroyed) here */
     double *vecA, *vecB, *vecC, *vecD;
 } kkt_cuda;
 
@@ -111,10 +112,11 @@ extern hdsdp_retcode HKKTInit( hdsdp_kkt *HKKT, int nRow, int nCones, hdsdp_cone
     if ( !kc ) return HDSDP_RETCODE_MEMORY;
     kc->nCones = nCones;
     kc->dcone = (void **) calloc(nCones > 0 ? nCones : 1, sizeof(void *));
+    kc->ownsLp = (int *) calloc(nCones > 0 ? nCones : 1, sizeof(int));
     kc->vecA = (double *) calloc(nRow, sizeof(double)); kc->vecB = (double *) calloc(nRow, sizeof(double));
     kc->vecC = (double *) calloc(nRow, sizeof(double)); kc->vecD = (double *) calloc(nRow, sizeof(double));
-    if ( !kc->dcone || !kc->vecA || !kc->vecB || !kc->vecC || !kc->vecD || table_insert(HKKT, kc) != 0 ) {
-        free(kc->dcone); free(kc->vecA); free(kc->vecB); free(kc->vecC); free(kc->vecD); free(kc);
+    if ( !kc->dcone || !kc->ownsLp || !kc->vecA || !kc->vecB || !kc->vecC || !kc->vecD || table_insert(HKKT, kc) != 0 ) {
+        free(kc->dcone); free(kc->ownsLp); free(kc->vecA); free(kc->vecB); free(kc->vecC); free(kc->vecD); free(kc);
         return HDSDP_RETCODE_MEMORY;
     }
     int drc = hdsdpcu_kkt_create(&kc->dkkt, nRow);
@@ -131,6 +133,7 @@ extern hdsdp_retcode HKKTInit( hdsdp_kkt *HKKT, int nRow, int nCones, hdsdp_cone
         } else if ( c->cone == HDSDP_CONETYPE_LP ) {
             if ( hdsdpcu_lp_create(&kc->dcone[iCone], nRow, u->nConicCol, u->coneMatBeg, u->coneMatIdx, u->coneMatElem) != 0 )
                 return HDSDP_RETCODE_FAILED;
+            kc->ownsLp[iCone] = 1;
         } else {
             printf("[hdsdpcu] unsupported cone type %d in HKKTInit\n", (int) c->cone);
             return HDSDP_RETCODE_FAILED;
@@ -295,11 +298,12 @@ extern void HKKTClear( hdsdp_kkt *HKKT ) {
     if ( kc ) {
         for ( int i = 0; i < kc->nCones; ++i ) {
             if ( !kc->dcone[i] ) continue;
-            /* SDP cone images belong to the cone hook (destroyed by coneDestroyData) */
-            if ( HKKT->cones && HKKT->cones[i] && HKKT->cones[i]->cone == HDSDP_CONETYPE_LP ) hdsdpcu_lp_destroy(&kc->dcone[i]);
+            /* SDP cone images belong to the cone hook (destroyed by coneDestroyData).  HDSDPClear (interface/hdsdp.c:943-950)
+               frees the cones and their array BEFORE the Schur object, so HKKT->cones must not be touched here. */
+            if ( kc->ownsLp[i] ) hdsdpcu_lp_destroy(&kc->dcone[i]);
         }
         hdsdpcu_kkt_destroy(&kc->dkkt);
-        free(kc->dcone);
+        free(kc->dcone); free(kc->ownsLp);
         free(kc->vecA); free(kc->vecB); free(kc->vecC); free(kc->vecD); free(kc);
         for ( int i = 0; i < g_cap; ++i ) if ( g_keys[i] == HKKT ) { g_keys[i] = NULL; g_vals[i] = NULL; }
         shim_prof_report();
