@@ -686,9 +686,14 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
             HD_CUDA(cudaMemcpy(c->d_dn_full + (size_t) d * np * np, full.data(), sizeof(double) * full.size(), cudaMemcpyHostToDevice));
         }
         HD_CALL(upload(&c->d_dn_con, d_con));
-        if (c->nd >= DD_MIN) {
+        // batched dense x dense block: three [ndp x np^2] workspaces.  Only when they fit comfortably (a third of the free HBM,
+        // grid limits of dd_swap_kernel); otherwise d_dn_vec stays null and the build uses the per-row explicit-B path.
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t dd_bytes = sizeof(double) * (size_t) hd_pad(c->nd) * np * np;
+        if (c->nd >= DD_MIN && np <= 65535 && 3 * dd_bytes <= free_b / 3) {
             c->ndp = hd_pad(c->nd);
-            const size_t bytes = sizeof(double) * (size_t) c->ndp * np * np;
+            const size_t bytes = dd_bytes;
             HD_CUDA(cudaMalloc(&c->d_dn_vec, bytes)); HD_CUDA(cudaMalloc(&c->d_dn_U, bytes)); HD_CUDA(cudaMalloc(&c->d_dn_Ut, bytes));
             HD_CUDA(cudaMalloc(&c->d_dn_G, sizeof(double) * (size_t) c->ndp * c->ndp));
             HD_CUDA(cudaMemset(c->d_dn_vec, 0, bytes));

@@ -49,22 +49,22 @@ __global__ void min_vec_kernel(const double *__restrict__ v, int n, double *out)
 
 // copy the lower trapezoids of the block columns owned by this rank (rows >= the block's first row)
 __global__ void copy_owned_kernel(double *__restrict__ dst, const double *__restrict__ src, long ld, int mp, int nb, int rank, int nranks) {
-    const int col = blockIdx.y;
+    const int col = blockIdx.x;   // columns on gridDim.x (no 65535 limit)
     if ((col / nb) % nranks != rank) return;
     const int r0 = (col / nb) * nb;
-    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < mp; r += gridDim.x * blockDim.x)
+    for (int r = r0 + blockIdx.y * blockDim.x + threadIdx.x; r < mp; r += gridDim.y * blockDim.x)
         dst[(long) col * ld + r] = src[(long) col * ld + r];
 }
 
 // M <- 0 on the part that is ever read: rows >= the first row of each 128-column block, and only the block columns this
 // rank owns (HKKTClean memsets all of M, hdsdp_schur.c:156-162; the strict upper triangle is never referenced)
 __global__ void zero_lower_kernel(double *M, long ld, int mp, int nb, int rank, int nranks) {
-    const int col = blockIdx.y;
+    const int col = blockIdx.x;   // columns on gridDim.x (no 65535 limit)
     if (nranks > 1 && (col / nb) % nranks != rank) return;
     const int r0 = (col / HD_LEAF) * HD_LEAF;
     double2 *p = reinterpret_cast<double2 *>(M + (long) col * ld + r0);
     const int cnt = (mp - r0) / 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) p[i] = make_double2(0.0, 0.0);
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < cnt; i += gridDim.y * blockDim.x) p[i] = make_double2(0.0, 0.0);
 }
 
 __global__ void add_diag_vec_kernel(double *M, long ld, int m, const double *__restrict__ d) {
@@ -161,7 +161,7 @@ int kkt_clean(KktCU *k, int typeKKT) {
     }
     HD_CUDA(cudaMemsetAsync(k->d_scal + 3, 0, sizeof(double), st));
     if (typeKKT == KKT_INFEASIBLE || typeKKT == KKT_HOMOGENEOUS || typeKKT == KKT_PRIMAL) {
-        HDK(zero_lower_kernel)<<<dim3(16, k->mp), 256, 0, st>>>(k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
+        HDK(zero_lower_kernel)<<<dim3(k->mp, 16), 256, 0, st>>>(k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
         HD_CUDA(cudaGetLastError());
         k->factored = false;
         k->fresh = true;
@@ -255,12 +255,12 @@ int kkt_export(KktCU *k, double *asinv, double *asinvrd, double *asinvc, double 
 }
 
 // HKKTFactorize: copy M (lower) into the factor buffer, pad, Cholesky.  info > 0 -> HD_FAILED
-// (the reference would fall back to dsytrf LDL here, hdsdp_linsolver.c:2036-2039; not built yet)
+// (the reference falls back to dsytrf LDL there, hdsdp_linsolver.c:2036-2039: here the LDL^T mode of chol.cu, see below)
 int kkt_factorize(KktCU *k, int *info_out) {
     cudaStream_t st = hd_stream();
     if (k->dist && k->nranks > 1) {
         // multi-GPU: this rank's block columns of M go into the factor buffer, the peers' columns arrive as factor panels
-        HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
+        HDK(copy_owned_kernel)<<<dim3(k->mp, 8), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
         HD_CUDA(cudaGetLastError());
         HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
         int info = 0;
@@ -268,7 +268,7 @@ int kkt_factorize(KktCU *k, int *info_out) {
         if (rc == HD_OK && info > 0 && !k->chol->ldl) {
             // every rank sees the same info (it travels with the panels): all switch to LDL^T together, for good
             fprintf(stderr, "[hdsdpcu] KKT system is almost indefinite (pivot %d). Switch to LDL.\n", info);
-            HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
+            HDK(copy_owned_kernel)<<<dim3(k->mp, 8), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
             HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
             rc = dist_factor(k->dist, &info, true);
         }
@@ -277,7 +277,7 @@ int kkt_factorize(KktCU *k, int *info_out) {
         return k->factored ? HD_OK : HD_FAILED;
     }
     // only the lower trapezoids are ever read by the factorisation: half the traffic of a full copy
-    HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, HD_LEAF, 0, 1);
+    HDK(copy_owned_kernel)<<<dim3(k->mp, 8), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, HD_LEAF, 0, 1);
     HD_CUDA(cudaGetLastError());
     HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
     int info = 0;
@@ -287,7 +287,7 @@ int kkt_factorize(KktCU *k, int *info_out) {
         // -- permanently, as HFpLinsysSwitchToIndefinite does.  Here: unpivoted LDL^T with static pivoting on the GPU.
         fprintf(stderr, "[hdsdpcu] KKT system is almost indefinite (pivot %d). Switch to LDL.\n", info);
         k->chol->ldl = true;
-        HDK(copy_owned_kernel)<<<dim3(8, k->mp), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, HD_LEAF, 0, 1);
+        HDK(copy_owned_kernel)<<<dim3(k->mp, 8), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, HD_LEAF, 0, 1);
         HD_CALL(hd_pad_identity(st, k->chol->L, k->mp, k->m, k->mp));
         HD_CALL(chol_factor(st, k->chol, &info));
     }

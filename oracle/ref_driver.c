@@ -259,6 +259,18 @@ int refdrv_solve_rhs(refdrv *h, const double *rhs, double *sol) {
     return (int) HKKTSolve(h->kkt, (double *) rhs, sol);
 }
 
+/* State of the reference's default solver of M after the last HKKTSolve (conjGradLinSolver, linalg/hdsdp_linsolver.c:1289-1660):
+ * out[0] = useJacobi (1: diagonal preconditioner still in use; 0: PCG failed once and a dpotrf of a copy of M is the
+ * preconditioner from then on, :1558-1567), out[1] = CG iterations of the last solve, out[2] = number of solves,
+ * out[3] = status of the last solve (iter_status).  Returns nonzero if M is not held by the dense iterative back-end. */
+int refdrv_cg_status(refdrv *h, int *out) {
+    if (!h->kkt || h->kkt->isKKTSparse || !h->kkt->kktM || h->kkt->kktM->LinType != HDSDP_LINSYS_DENSE_ITERATIVE) return 1;
+    iterative_linsys *it = (iterative_linsys *) h->kkt->kktM->chol;
+    if (!it) return 1;
+    out[0] = it->useJacobi; out[1] = it->nIters; out[2] = it->nSolves; out[3] = (int) it->solStatus;
+    return 0;
+}
+
 /* Time nRep x { HKKTBuildUp, [Regularize], HKKTFactorize, nSolve x HKKTSolve } on the host.
  * times[0..3] = seconds in build / factorize / solves / total (averaged over nRep). */
 int refdrv_time_iteration(refdrv *h, int typeKKT, double reg, int nSolve, int nRep, double *times) {

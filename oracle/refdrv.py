@@ -60,6 +60,8 @@ def lib():
         l.refdrv_factorize.argtypes = [c_void_p]
         l.refdrv_solve_rhs.argtypes = [c_void_p, c_double_p, c_double_p]
         l.refdrv_time_iteration.argtypes = [c_void_p, c_int, c_double, c_int, c_int, c_double_p]
+        if hasattr(l, "refdrv_cg_status"):
+            l.refdrv_cg_status.argtypes = [c_void_p, c_int_p]
         l.refdrv_register_primal.argtypes = [c_void_p, POINTER(c_double_p)]
         l.refdrv_destroy.argtypes = [c_void_p]
         l.refdrv_optimize.argtypes = [c_int, c_int, c_int_p, c_int_p, POINTER(c_int_p), POINTER(c_int_p), POINTER(c_double_p),
@@ -203,6 +205,15 @@ class RefKKT:
         if rc != 0:
             raise RuntimeError(f"reference iteration failed rc={rc}")
         return {"build": t[0], "factorize": t[1], "solve": t[2], "total": t[3]}
+
+    def cg_status(self):
+        """The reference's PCG-on-M state after the last solve: did it fall back to a Cholesky preconditioner?"""
+        if not hasattr(self.l, "refdrv_cg_status"):
+            return None
+        out = np.zeros(4, dtype=np.int32)
+        if self.l.refdrv_cg_status(self.h, _ip(out)) != 0:
+            return None
+        return {"use_jacobi": int(out[0]), "n_iters": int(out[1]), "n_solves": int(out[2]), "status": int(out[3])}
 
     def close(self):
         if self.h:

@@ -1,0 +1,197 @@
+"""Parity where the real kernels run: sizes far above one 128 x 128 leaf, against the UNMODIFIED reference
+run live on the same box (oracle/_ref through oracle/refdrv.py) and against LAPACK on ill-conditioned inputs.
+
+ (b) theta n = 1500, m = 8001 at bench.py's iterate: the device's S, log det, Schur matrix M (all 32 M lower entries), side vectors
+     (INFEASIBLE and HOMOGENEOUS types) and solve against refdrv.RefKKT on the same y.   Gate: 1e-10 relative (north star).
+ (c) ill-conditioned factorisations: synthetic SPD matrices with condition 1e10 / 1e12 / 1e14 at n = 1024 and 4096 (the
+     recursion multiplies by explicit 128 x 128 leaf inverses, csrc/chol.cu) against LAPACK's dpotrf / dpotri / dpotrs:
+     backward errors must stay within a small factor of LAPACK's own;  and S, M at the FINAL iterate of a real IPM solve
+     (theta n = 200, m = 3001 through the drop-in build; cond(S) ~ 1e8..1e10), compared with the reference at the same y with the
+     tolerance scaled by cond(S) * eps (two backward-stable algorithms agree no better than that).
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def entry_ok(got, ref, rtol, what):
+    s = np.abs(ref).max()
+    err = np.abs(got - ref)
+    tol = rtol * np.maximum(np.abs(ref), 1e-3 * s)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} entries differ, max err {err.max():.3e} (scale {s:.3e}, rtol {rtol:.1e})"
+
+
+def need_ref():
+    from oracle import refdrv
+    if not refdrv.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return refdrv
+
+
+def test_theta_n1500_m8001_against_live_reference():
+    import bench
+    from hdsdp_b200 import api, problem
+    refdrv = need_ref()
+    n, ne = 1500, 8000
+    prob = problem.gen_theta(n, ne, seed=2)
+    m = prob.m
+    y = bench.theta_point(m, n, 0)
+    ref = refdrv.RefKKT(prob)
+    ld_ref = ref.set_point(y, bench.TAU, bench.RD)
+    sdp, lps, kkt = api.build_problem(prob)
+    cone = sdp[0]
+    cone.set_start(bench.RD)
+    cone.update(bench.TAU, y)
+    assert cone.factorize()
+    # S and its factor
+    entry_ok(np.tril(cone.get_buffer(api.BUFFER_DUALVAR)), np.tril(ref.get_S(0)), 1e-13, "S")
+    np.testing.assert_allclose(cone.get_factor_diag(), ref.get_Ldiag(0), rtol=1e-10)
+    assert abs(cone.get_log_barrier(bench.TAU, None) - ld_ref) <= 1e-10 * abs(ld_ref)
+    for type_kkt in (api.KKT_TYPE_INFEASIBLE, api.KKT_TYPE_HOMOGENEOUS):
+        ref.build(type_kkt)
+        kkt.build_up(type_kkt)
+        M = np.tril(kkt.get_matrix())
+        entry_ok(M, np.tril(ref.get_M()), 1e-10, f"Schur matrix (type {type_kkt}, m = {m})")
+        v, vr = kkt.export(), ref.get_vectors()
+        names = ["dASinvVec", "dASinvRdSinvVec"] + (["dASinvCSinvVec"] if type_kkt == api.KKT_TYPE_HOMOGENEOUS else [])
+        for k in names:
+            entry_ok(v[k], vr[k], 1e-10, k)
+        scal = ["dTraceSinv"] + (["dCSinvCSinv", "dCSinv", "dCSinvRdSinv"] if type_kkt == api.KKT_TYPE_HOMOGENEOUS else [])
+        for k in scal:
+            assert abs(v[k] - vr[k]) <= 1e-10 * max(abs(vr[k]), 1e-300), (k, v[k], vr[k])
+    # regularize + factorize + solve (the reference answers with its PCG: 1e-6 is its own accuracy)
+    ref.regularize(bench.KKT_REG)
+    kkt.regularize(bench.KKT_REG)
+    entry_ok(np.diag(kkt.get_matrix()), np.diag(ref.get_M()), 1e-10, "diag(M) after HKKTRegularize")
+    assert ref.factorize() == 0 and kkt.factorize() == 0
+    xr, x = ref.solve(prob.rhs), kkt.solve(prob.rhs)
+    assert np.abs(x - xr).max() <= 1e-6 * np.abs(xr).max()
+    # the direct solve must satisfy the system the REFERENCE assembled to (much) better than the PCG answer does
+    Mr = ref.get_M()
+    Mr = np.tril(Mr) + np.tril(Mr, -1).T
+    r_gpu = np.abs(Mr @ x - prob.rhs).max()
+    r_ref = np.abs(Mr @ xr - prob.rhs).max()
+    assert r_gpu <= max(r_ref, 1e-10 * np.abs(prob.rhs).max()), (r_gpu, r_ref)
+    # ratio test at n = 1500 (12 leaves): device Lanczos against the reference's
+    dy = np.random.RandomState(5).standard_normal(m) * 0.01
+    a_ref = ref.ratio_test(0, 0.0, dy, 0.0, 0)
+    a_gpu = cone.ratio_test(0.0, dy, 0.0, api.BUFFER_DUALVAR)
+    assert abs(a_gpu - a_ref) <= 1e-3 * abs(a_ref), (a_gpu, a_ref)     # the method's own stopping accuracy
+    ref.close(); kkt.close(); cone.close()
+
+
+def spd_with_cond(n, cond, seed):
+    rs = np.random.RandomState(seed)
+    Q, _ = np.linalg.qr(rs.standard_normal((n, n)))
+    ev = np.logspace(0, -np.log10(cond), n)
+    A = (Q * ev) @ Q.T
+    return 0.5 * (A + A.T)
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+@pytest.mark.parametrize("cond", [1e10, 1e12, 1e14])
+def test_ill_conditioned_factor_inverse_solve_against_lapack(n, cond):
+    import scipy.linalg as sla
+    from hdsdp_b200.api import DenseLinsys
+    A = spd_with_cond(n, cond, seed=n + int(np.log10(cond)))
+    nrmA = np.linalg.norm(A, 2)
+    eps = np.finfo(float).eps
+    try:
+        Lr = sla.cholesky(A, lower=True)
+    except np.linalg.LinAlgError:
+        pytest.skip("not numerically positive definite for LAPACK either (cond * n * eps > 1)")
+    margin = (np.diag(Lr).min() ** 2) / (n * eps * nrmA)      # how far LAPACK's smallest pivot is above the rounding level
+    ls = DenseLinsys(n)
+    rc = ls.numeric(np.asfortranarray(A))
+    if rc != 0 and margin < 10.0:
+        pytest.skip(f"smallest pivot within 10 n eps ||A|| of zero (margin {margin:.1f}): either outcome is legitimate")
+    assert rc == 0, f"a positive definite matrix must factor (LAPACK does, pivot margin {margin:.1f})"
+    # factor: L itself is only determined to cond * eps, so the diagonal is a sanity check; the gates are the backward errors
+    L_diag = ls.get_diag()
+    assert (L_diag > 0).all()
+    np.testing.assert_allclose(L_diag, np.diag(Lr), rtol=min(0.5, 100 * cond * eps + 1e-10))
+    rs = np.random.RandomState(3)
+    b = rs.standard_normal(n)
+    x = ls.solve(b)
+    xr = sla.cho_solve((Lr, True), b)
+    be_gpu = np.linalg.norm(A @ x - b) / (nrmA * np.linalg.norm(x))
+    be_ref = np.linalg.norm(A @ xr - b) / (nrmA * np.linalg.norm(xr))
+    assert be_gpu <= max(20.0 * be_ref, 100 * eps), f"solve backward error {be_gpu:.2e} vs LAPACK {be_ref:.2e}"
+    # triangular solves separately (Lanczos operator)
+    f = ls.fsolve(b)
+    fr = sla.solve_triangular(Lr, b, lower=True)
+    bf_gpu = np.linalg.norm(Lr @ f - b) / (np.linalg.norm(Lr, 2) * np.linalg.norm(f))
+    bf_ref = np.linalg.norm(Lr @ fr - b) / (np.linalg.norm(Lr, 2) * np.linalg.norm(fr))
+    assert bf_gpu <= max(50.0 * bf_ref, 1e4 * eps), f"forward-substitution backward error {bf_gpu:.2e} vs LAPACK {bf_ref:.2e}"
+    # inverse (dpotri twin): residual ||A X - I|| against LAPACK's own
+    X = ls.invert()
+    Xr = np.linalg.inv(A)
+    res_gpu = np.linalg.norm(A @ X - np.eye(n)) / (nrmA * np.linalg.norm(X))
+    res_ref = np.linalg.norm(A @ Xr - np.eye(n)) / (nrmA * np.linalg.norm(Xr))
+    assert res_gpu <= max(20.0 * res_ref, 100 * eps * np.sqrt(n)), f"inverse residual {res_gpu:.2e} vs LAPACK {res_ref:.2e}"
+    assert np.abs(X - X.T).max() == 0.0
+    ls.close()
+
+
+def test_late_iterate_S_and_M_of_a_real_solve():
+    """S and M at the final iterate of a full IPM solve (theta n = 200, m = 3001 through the drop-in build)."""
+    sys.path.insert(0, ROOT)
+    from tools import fullsolve
+    from hdsdp_b200 import api, problem
+    refdrv = need_ref()
+    if not os.path.exists(fullsolve.INTEGRATED):
+        pytest.skip("integration/_build/libhdsdp_integrated.so not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        ypath = os.path.join(tmp, "y.npy")
+        res, log, err = fullsolve.run(("theta", 200, 3000), True, 1, dump_y=ypath)
+        assert res is not None and res["retcode"] == 0, log[-2000:] + err[-2000:]
+        y = np.load(ypath)
+    prob = problem.gen_theta(200, 3000, seed=2)
+    m, n = prob.m, 200
+    # feasible phase: S = C - A'y (tau = 1, Rd = 0); perturbation as the solver uses at the end (dPerturb ~ 1e-10 .. 0)
+    ref = refdrv.RefKKT(prob)
+    RD_LATE = -1e-7      # S = 1e-7 I + C - A'y: the final iterate sits on the boundary of the cone up to the solver's perturbation
+    ref.set_point(y, 1.0, RD_LATE)
+    Sr = ref.get_S(0)
+    Sr = np.tril(Sr) + np.tril(Sr, -1).T
+    w = np.linalg.eigvalsh(Sr)
+    assert w[0] > 0
+    cond = w[-1] / w[0]
+    assert cond > 1e5, f"expected an ill-conditioned late-iterate S, cond = {cond:.2e}"
+    sdp, lps, kkt = api.build_problem(prob)
+    cone = sdp[0]
+    cone.set_start(RD_LATE)
+    cone.update(1.0, y)
+    assert cone.factorize()
+    eps = np.finfo(float).eps
+    tol = max(1e-10, 50.0 * cond * eps)
+    ref.build(api.KKT_TYPE_INFEASIBLE)
+    kkt.build_up(api.KKT_TYPE_INFEASIBLE)
+    Mg, Mr = np.tril(kkt.get_matrix()), np.tril(ref.get_M())
+    entry_ok(Mg, Mr, tol, f"late-iterate Schur matrix (cond(S) = {cond:.2e})")
+    v, vr = kkt.export(), ref.get_vectors()
+    entry_ok(v["dASinvVec"], vr["dASinvVec"], tol, "late-iterate dASinvVec")
+    # S^-1 against extended-precision-free ground truth: residual of S S^-1 = I
+    Si = cone.get_sinv()
+    res = np.linalg.norm(Sr @ Si - np.eye(n)) / (np.linalg.norm(Sr, 2) * np.linalg.norm(Si, 2))
+    assert res <= 100 * eps * np.sqrt(n), res
+    # Cholesky of the late-iterate M (m = 3001, 24 leaves) and solve: backward error against LAPACK's
+    import scipy.linalg as sla
+    Mfull = Mr + np.tril(Mr, -1).T
+    assert kkt.factorize() == 0
+    b = prob.rhs + 0.1 * np.random.RandomState(9).standard_normal(m)
+    x = kkt.solve(b)
+    Mgf = Mg + np.tril(Mg, -1).T
+    be_gpu = np.linalg.norm(Mgf @ x - b) / (np.linalg.norm(Mgf, 2) * np.linalg.norm(x))
+    xr = sla.cho_solve(sla.cho_factor(Mgf, lower=True), b)
+    be_ref = np.linalg.norm(Mgf @ xr - b) / (np.linalg.norm(Mgf, 2) * np.linalg.norm(xr))
+    assert be_gpu <= max(20.0 * be_ref, 100 * eps), (be_gpu, be_ref, np.linalg.cond(Mfull))
+    ref.close(); kkt.close(); cone.close()

@@ -38,6 +38,9 @@ else:
     raise SystemExit("unknown problem kind " + kind)
 t0 = time.time()
 res = refdrv.optimize(prob, max_iter={max_iter})
+if {dump_y!r}:
+    import numpy as np
+    np.save({dump_y!r}, res["y"])
 print("RESULT " + json.dumps({{"m": prob.m, "n": [c.dim for c in prob.cones], "pObj": res["pObj"], "dObj": res["dObj"],
                               "iterations": res["iterations"], "status": res["status"], "retcode": res["retcode"],
                               "dimacs": list(res["dimacs"]), "seconds": res["seconds"], "wall": time.time() - t0}}))
@@ -49,13 +52,13 @@ def parse_spec(s):
     return p[0], int(p[1]), int(p[2])
 
 
-def run(spec, integrated, threads, max_iter=0, timeout=3000):
+def run(spec, integrated, threads, max_iter=0, timeout=3000, dump_y=""):
     env = dict(os.environ, OPENBLAS_NUM_THREADS=str(threads))
     if integrated:
         env["HDSDP_REFDRV_LIB"] = INTEGRATED
     else:
         env.pop("HDSDP_REFDRV_LIB", None)
-    code = HELPER.format(root=ROOT, spec=spec, max_iter=max_iter)
+    code = HELPER.format(root=ROOT, spec=spec, max_iter=max_iter, dump_y=dump_y)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=timeout)
     res = None
     for ln in out.stdout.splitlines():
