@@ -332,6 +332,18 @@ class KKT:
         check(self.lib.hdsdpcu_kkt_solve_many(self.h, r.shape[1], _dp(r), _dp(out)), "HKKTSolve")
         return out
 
+    def symv(self, x: np.ndarray) -> np.ndarray:
+        """y = M x on the device-resident Schur matrix."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(self.m)
+        check(self.lib.hdsdpcu_kkt_symv(self.h, _dp(x), _dp(y)), "symv")
+        return y
+
+    def solve_status(self):
+        r = c_double(0.0); s = c_int(0)
+        self.lib.hdsdpcu_kkt_solve_status(self.h, byref(r), byref(s))
+        return r.value, s.value
+
     def register_psdp(self, Xs: List[np.ndarray]):
         self._primal_keep = [np.asfortranarray(X, dtype=np.float64) for X in Xs]
         arr = (c_double_p * len(Xs))(*[_dp(X) for X in self._primal_keep])

@@ -533,6 +533,25 @@ int hdsdpcu_kkt_ldl_status(void *kkt, int *isLdl, int *nNegative, int *nPerturbe
     if (nPerturbed) *nPerturbed = k->chol->ldl ? k->chol->nperturbed : 0;
     return HD_OK;
 }
+int hdsdpcu_kkt_symv(void *kkt, const double *x, double *y) {
+    // y = M x with the assembled Schur matrix (lower triangle in HBM): the dsymv of the reference's PCG loop; test / PCG building block
+    KktCU *k = (KktCU *) kkt;
+    const size_t bytes = sizeof(double) * (size_t) k->mp;
+    memset(k->h_vec, 0, 2 * bytes);
+    memcpy(k->h_vec, x, sizeof(double) * k->m);
+    HD_CUDA(cudaMemcpyAsync(k->d_rhs, k->h_vec, 2 * bytes, cudaMemcpyHostToDevice, g_stream));
+    HD_CALL(kkt_symv_dev(k, k->d_rhs, k->d_rhs + k->mp, 1));
+    HD_CUDA(cudaMemcpyAsync(k->h_vec, k->d_rhs + k->mp, bytes, cudaMemcpyDeviceToHost, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
+    memcpy(y, k->h_vec, sizeof(double) * k->m);
+    return HD_OK;
+}
+int hdsdpcu_kkt_solve_status(void *kkt, double *relResidual, int *refineSteps) {
+    KktCU *k = (KktCU *) kkt;
+    if (relResidual) *relResidual = k->last_residual;
+    if (refineSteps) *refineSteps = k->last_refine_steps;
+    return HD_OK;
+}
 int hdsdpcu_kkt_solve(void *kkt, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, 1, rhs, lhs); }
 int hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *rhs, double *lhs) { return kkt_solve((KktCU *) kkt, nRhs, rhs, lhs); }
 void hdsdpcu_kkt_registerpsdp(void *kkt, int nCones, double **X) {

@@ -784,6 +784,10 @@ int chol_dsolve(cudaStream_t st, DenseChol *c, double *x, int nrhs, long ldx) {
 }
 
 int chol_invert(cudaStream_t st, DenseChol *c, double *inv) {
+    if (c->ldl) { // X X^T would drop J = diag(+-1): the inverse of an L J L^T factor is not provided (nothing on the path needs it)
+        fprintf(stderr, "[hdsdpcu] chol_invert: not available for an LDL^T factorisation\n");
+        return HD_FAILED;
+    }
     HD_CALL(chol_ensure_work(c));
     // X = L^-T (upper triangular) in work; blocks below the diagonal leaves must read as zero
     HD_CUDA(cudaMemsetAsync(c->work, 0, (size_t) c->np * c->np * sizeof(double), st));

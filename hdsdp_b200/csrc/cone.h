@@ -122,6 +122,9 @@ struct KktCU {
     int rank = 0, nranks = 1, shard_nb = HD_LEAF;
     struct DistChol *dist = nullptr; // distributed factorisation of M (dist.cu); null on one GPU
     double *d_gather = nullptr;      // [16 x 8] all-gather scratch
+    double *d_ref = nullptr;         // [mp x 8] right-hand sides + residuals of the refined LDL^T solves
+    double last_residual = 0.0;      // max |b - M x| / max |b| of the last refined solve
+    int last_refine_steps = 0;
 };
 
 cudaStream_t hd_stream();
@@ -166,5 +169,6 @@ int kkt_export(KktCU *k, double *asinv, double *asinvrd, double *asinvc, double 
                double *tracesinv);
 int kkt_factorize(KktCU *k, int *info_out);
 int kkt_solve_dev(KktCU *k, double *d_x, int nRhs);
+int kkt_symv_dev(KktCU *k, const double *d_x, double *d_y, int nRhs);
 int kkt_solve(KktCU *k, int nRhs, const double *rhs, double *lhs);
 int kkt_get_matrix(KktCU *k, double *Mhost);

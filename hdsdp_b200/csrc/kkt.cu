@@ -104,6 +104,103 @@ __global__ void lp_schur_kernel(const int *__restrict__ colptr, const int *__res
     }
 }
 
+// y += M x for a symmetric M of which only the lower triangle is stored (the dsymv('L') of the reference's PCG loop,
+// linalg/hdsdp_linsolver.c:1446-1588), nrhs <= 2 vectors.  HBM-bound: every 128 x 128 tile of the lower triangle is read ONCE
+// (4 m^2 bytes) and used for both y_i += T x_j and y_j += T^T x_i.  One CTA (256 threads) per tile: thread (row, half) holds
+// 64 entries of its tile row in registers (coalesced loads, all in flight together); the row product is reduced over the two
+// halves through shared memory, the column products over the 32 lanes by shuffles and over the 4 warps of a half through
+// shared memory; results are added to y with atomics.
+template <int NRHS>
+__global__ void __launch_bounds__(256) symv_lower_kernel(const double *__restrict__ M, long ld, int nblk, const double *__restrict__ x,
+                                                        long ldx, double *y, long ldy) {
+    __shared__ double xi[NRHS][HD_LEAF], xj[NRHS][HD_LEAF];
+    __shared__ double rowred[NRHS][2][HD_LEAF];
+    __shared__ double colred[NRHS][4][HD_LEAF];
+    // tile (i, j), i >= j, from the linear index: i = floor((sqrt(8 b + 1) - 1) / 2)
+    const long b = blockIdx.x;
+    int i = (int) ((sqrt(8.0 * (double) b + 1.0) - 1.0) * 0.5);
+    while ((long) (i + 1) * (i + 2) / 2 <= b) ++i;
+    while ((long) i * (i + 1) / 2 > b) --i;
+    const int j = (int) (b - (long) i * (i + 1) / 2);
+    if (i >= nblk) return;
+    const int t = threadIdx.x, row = t & 127, half = t >> 7, lane = t & 31, w4 = (t >> 5) & 3;
+    const bool diag = (i == j);
+    const double *T = M + ((long) j * HD_LEAF + half * 64) * ld + (long) i * HD_LEAF + row;
+    double tl[64];
+#pragma unroll
+    for (int q = 0; q < 64; ++q) tl[q] = __ldcs(&T[(long) q * ld]);
+    if (t < HD_LEAF) {
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            xi[r][t] = x[(long) r * ldx + (long) i * HD_LEAF + t];
+            xj[r][t] = x[(long) r * ldx + (long) j * HD_LEAF + t];
+        }
+    }
+    if (diag) { // only the lower triangle of a diagonal tile is data
+#pragma unroll
+        for (int q = 0; q < 64; ++q) if (half * 64 + q > row) tl[q] = 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 64; ++q) acc += tl[q] * xj[r][half * 64 + q];
+        rowred[r][half][row] = acc;
+    }
+    // transposed part: column c = half*64 + q gets sum_row T[row, c] x_i[row]; on a diagonal tile the diagonal itself
+    // was already used by the row product
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) {
+        const double xv = xi[r][row];
+#pragma unroll
+        for (int q = 0; q < 64; ++q) {
+            double v = tl[q] * xv;
+            if (diag && half * 64 + q == row) v = 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == (q & 31)) colred[r][w4][half * 64 + q] = v;
+        }
+    }
+    __syncthreads();
+    if (t < HD_LEAF) {
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            atomicAdd(&y[(long) r * ldy + (long) i * HD_LEAF + t], rowred[r][0][t] + rowred[r][1][t]);
+            atomicAdd(&y[(long) r * ldy + (long) j * HD_LEAF + t], colred[r][0][t] + colred[r][1][t] + colred[r][2][t] + colred[r][3][t]);
+        }
+    }
+}
+
+// r <- b - r (r holds M x), and max |r_i| / max |b_i| per vector into out[2 v], out[2 v + 1]
+__global__ void residual_finish_kernel(double *r, const double *__restrict__ b, long ld, int m, int nrhs, double *out) {
+    __shared__ double red[2][256];
+    const int v = blockIdx.x;
+    double mr = 0.0, mb = 0.0;
+    for (int i = threadIdx.x; i < m; i += 256) {
+        const double bi = b[(long) v * ld + i];
+        const double ri = bi - r[(long) v * ld + i];
+        r[(long) v * ld + i] = ri;
+        mr = fmax(mr, fabs(ri)); mb = fmax(mb, fabs(bi));
+        if (ri != ri) mr = INFINITY;
+    }
+    red[0][threadIdx.x] = mr; red[1][threadIdx.x] = mb;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            red[0][threadIdx.x] = fmax(red[0][threadIdx.x], red[0][threadIdx.x + o]);
+            red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[2 * v] = red[0][0]; out[2 * v + 1] = red[1][0]; }
+}
+
+__global__ void vec_add2_kernel(double *x, const double *__restrict__ d, long ld, int m, int nrhs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) for (int v = 0; v < nrhs; ++v) x[(long) v * ld + i] += d[(long) v * ld + i];
+}
+
 inline unsigned nblk(long total, int threads) { return (unsigned) ((total + threads - 1) / threads); }
 
 } // namespace
@@ -129,9 +226,9 @@ int kkt_create(KktCU **pk, int nRow) {
     HD_CUDA(cudaMemset(k->d_asinv, 0, sizeof(double) * k->mp));
     HD_CUDA(cudaMemset(k->d_asinvrd, 0, sizeof(double) * k->mp));
     HD_CUDA(cudaMemset(k->d_asinvc, 0, sizeof(double) * k->mp));
-    HD_CUDA(cudaMalloc(&k->d_scal, sizeof(double) * 8));
-    HD_CUDA(cudaMemset(k->d_scal, 0, sizeof(double) * 8));
-    HD_CUDA(cudaMallocHost(&k->h_scal, sizeof(double) * 8));
+    HD_CUDA(cudaMalloc(&k->d_scal, sizeof(double) * 16));
+    HD_CUDA(cudaMemset(k->d_scal, 0, sizeof(double) * 16));
+    HD_CUDA(cudaMallocHost(&k->h_scal, sizeof(double) * 16));
     HD_CUDA(cudaMalloc(&k->d_rhs, sizeof(double) * (size_t) k->mp * 8));
     HD_CUDA(cudaMemset(k->d_rhs, 0, sizeof(double) * (size_t) k->mp * 8));
     HD_CUDA(cudaMallocHost(&k->h_vec, sizeof(double) * (size_t) k->mp * 8));
@@ -146,6 +243,7 @@ void kkt_destroy(KktCU *k) {
     cudaFreeHost(k->h_scal); cudaFreeHost(k->h_vec);
     if (k->dist) dist_destroy(k->dist);
     if (k->d_gather) cudaFree(k->d_gather);
+    if (k->d_ref) cudaFree(k->d_ref);
     chol_destroy(k->chol);
     delete k;
 }
@@ -296,13 +394,70 @@ int kkt_factorize(KktCU *k, int *info_out) {
     return info == 0 ? HD_OK : HD_FAILED;
 }
 
-// nRhs device vectors of stride mp (padded with zeros) solved in place
+// y (nrhs vectors of stride mp) += M x, M = the assembled Schur matrix (lower triangle), single GPU only
+int kkt_symv_dev(KktCU *k, const double *d_x, double *d_y, int nRhs) {
+    if (k->dist && k->nranks > 1) return HD_FAILED; // every rank holds only its own block columns of M
+    cudaStream_t st = hd_stream();
+    const int nb = k->mp / HD_LEAF;
+    const long tiles = (long) nb * (nb + 1) / 2;
+    for (int r0 = 0; r0 < nRhs; r0 += 2) {
+        const int nr = (nRhs - r0 >= 2) ? 2 : 1;
+        ++g_hd_launches;
+        if (nr == 2) symv_lower_kernel<2><<<(unsigned) tiles, 256, 0, st>>>(k->d_M, k->mp, nb, d_x + (long) r0 * k->mp, k->mp, d_y + (long) r0 * k->mp, k->mp);
+        else symv_lower_kernel<1><<<(unsigned) tiles, 256, 0, st>>>(k->d_M, k->mp, nb, d_x + (long) r0 * k->mp, k->mp, d_y + (long) r0 * k->mp, k->mp);
+    }
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+static int solve_once(KktCU *k, cudaStream_t st, double *d_x, int nRhs) {
+    HD_CALL(chol_fsolve(st, k->chol, d_x, nRhs, k->mp));
+    HD_CALL(chol_dsolve(st, k->chol, d_x, nRhs, k->mp));
+    return chol_bsolve(st, k->chol, d_x, nRhs, k->mp);
+}
+
+// nRhs device vectors of stride mp (padded with zeros) solved in place.
+// LDL^T mode (static pivoting, no symmetric pivoting) on one GPU: M itself is intact, so the solve is followed by fixed-precision
+// iterative refinement on the residual b - M x (at most 3 steps) and FAILS if the residual does not come down to
+// 1e-9 max|b| -- a perturbed pivot or element growth can then never return an inaccurate Newton direction silently.
 int kkt_solve_dev(KktCU *k, double *d_x, int nRhs) {
     if (!k->factored) return HD_FAILED;
     cudaStream_t st = hd_stream();
-    HD_CALL(chol_fsolve(st, k->chol, d_x, nRhs, k->mp));
-    HD_CALL(chol_dsolve(st, k->chol, d_x, nRhs, k->mp));
-    HD_CALL(chol_bsolve(st, k->chol, d_x, nRhs, k->mp));
+    const bool refine = k->chol->ldl && !(k->dist && k->nranks > 1);
+    if (!refine) return solve_once(k, st, d_x, nRhs);
+    if (nRhs > 4) { // the refinement workspace holds 4 right-hand sides
+        for (int r0 = 0; r0 < nRhs; r0 += 4) HD_CALL(kkt_solve_dev(k, d_x + (size_t) r0 * k->mp, nRhs - r0 < 4 ? nRhs - r0 : 4));
+        return HD_OK;
+    }
+    const size_t bytes = sizeof(double) * (size_t) k->mp * nRhs;
+    if (!k->d_ref) HD_CUDA(cudaMalloc(&k->d_ref, sizeof(double) * (size_t) k->mp * 8));
+    double *d_b = k->d_ref, *d_r = k->d_ref + (size_t) 4 * k->mp;
+    HD_CUDA(cudaMemcpyAsync(d_b, d_x, bytes, cudaMemcpyDeviceToDevice, st));
+    HD_CALL(solve_once(k, st, d_x, nRhs));
+    k->last_refine_steps = 0;
+    for (int it = 0; it < 4; ++it) {
+        HD_CUDA(cudaMemsetAsync(d_r, 0, bytes, st));
+        HD_CALL(kkt_symv_dev(k, d_x, d_r, nRhs));
+        HDK(residual_finish_kernel)<<<nRhs, 256, 0, st>>>(d_r, d_b, k->mp, k->m, nRhs, k->d_scal + 8);
+        HD_CUDA(cudaMemcpyAsync(k->h_scal + 8, k->d_scal + 8, sizeof(double) * 2 * nRhs, cudaMemcpyDeviceToHost, st));
+        HD_CUDA(cudaStreamSynchronize(st));
+        double worst = 0.0;
+        for (int v = 0; v < nRhs; ++v) {
+            const double rel = k->h_scal[8 + 2 * v] / (k->h_scal[8 + 2 * v + 1] > 0.0 ? k->h_scal[8 + 2 * v + 1] : 1.0);
+            if (!(rel <= worst)) worst = rel;   // NaN propagates
+        }
+        k->last_residual = worst;
+        if (worst <= 1e-13) return HD_OK;
+        if (it == 3) break;
+        HD_CALL(solve_once(k, st, d_r, nRhs));
+        HDK(vec_add2_kernel)<<<nblk(k->m, 256), 256, 0, st>>>(d_x, d_r, k->mp, k->m, nRhs);
+        k->last_refine_steps = it + 1;
+    }
+    if (!(k->last_residual <= 1e-9)) {
+        fprintf(stderr, "[hdsdpcu] LDL^T solve of the Schur system: residual %.2e after %d refinement steps (%d perturbed pivots): FAILED\n",
+                k->last_residual, k->last_refine_steps, k->chol->nperturbed);
+        return HD_FAILED;
+    }
     return HD_OK;
 }
 
@@ -316,9 +471,27 @@ int kkt_solve(KktCU *k, int nRhs, const double *rhs, double *lhs) {
         memset(k->h_vec, 0, sizeof(double) * (size_t) k->mp * nb);
         for (int r = 0; r < nb; ++r) memcpy(k->h_vec + (size_t) r * k->mp, rhs + (size_t) (r0 + r) * m, sizeof(double) * m);
         HD_CUDA(cudaMemcpyAsync(k->d_rhs, k->h_vec, sizeof(double) * (size_t) k->mp * nb, cudaMemcpyHostToDevice, st));
-        HD_CALL(kkt_solve_dev(k, k->d_rhs, nb));
-        HD_CUDA(cudaMemcpyAsync(k->h_vec, k->d_rhs, sizeof(double) * (size_t) k->mp * nb, cudaMemcpyDeviceToHost, st));
-        HD_CUDA(cudaStreamSynchronize(st));
+        int rc = kkt_solve_dev(k, k->d_rhs, nb);
+        if (rc == HD_OK) {
+            HD_CUDA(cudaMemcpyAsync(k->h_vec, k->d_rhs, sizeof(double) * (size_t) k->mp * nb, cudaMemcpyDeviceToHost, st));
+            HD_CUDA(cudaStreamSynchronize(st));
+        }
+        // reference HFpLinsysSolve (linalg/hdsdp_linsolver.c:2088-2103): a failed solve or a NaN in sol[0] / rhs[0] makes the dense
+        // back-end of M switch to the indefinite factorisation for good ("KKT system is unstable. Switch to LDL.") and solve again
+        const bool bad = rc != HD_OK || k->h_vec[0] != k->h_vec[0] || rhs[(size_t) r0 * m] != rhs[(size_t) r0 * m];
+        if (bad && !k->chol->ldl && !(k->dist && k->nranks > 1)) {
+            fprintf(stderr, "[hdsdpcu] KKT system is unstable. Switch to LDL.\n");
+            k->chol->ldl = true;
+            HD_CALL(kkt_factorize(k, nullptr));
+            memset(k->h_vec, 0, sizeof(double) * (size_t) k->mp * nb);
+            for (int r = 0; r < nb; ++r) memcpy(k->h_vec + (size_t) r * k->mp, rhs + (size_t) (r0 + r) * m, sizeof(double) * m);
+            HD_CUDA(cudaMemcpyAsync(k->d_rhs, k->h_vec, sizeof(double) * (size_t) k->mp * nb, cudaMemcpyHostToDevice, st));
+            HD_CALL(kkt_solve_dev(k, k->d_rhs, nb));
+            HD_CUDA(cudaMemcpyAsync(k->h_vec, k->d_rhs, sizeof(double) * (size_t) k->mp * nb, cudaMemcpyDeviceToHost, st));
+            HD_CUDA(cudaStreamSynchronize(st));
+        } else if (bad) {
+            return HD_FAILED;
+        }
         double *out = lhs ? lhs : const_cast<double *>(rhs);
         for (int r = 0; r < nb; ++r) memcpy(out + (size_t) (r0 + r) * m, k->h_vec + (size_t) r * k->mp, sizeof(double) * m);
     }

@@ -188,7 +188,14 @@ int  hdsdpcu_kkt_export(void *kkt, double *dASinvVec, double *dASinvRdSinvVec, d
                         double *dCSinvCSinv, double *dCSinv, double *dCSinvRdSinv, double *dTraceSinv);
 int  hdsdpcu_kkt_factorize(void *kkt);   /* Cholesky; on a non-positive pivot switches (for good) to the LDL^T back-end */
 int  hdsdpcu_kkt_ldl_status(void *kkt, int *isLdl, int *nNegative, int *nPerturbed);
+/* solve: like HFpLinsysSolve (linalg/hdsdp_linsolver.c:2088-2103) a failed solve or a NaN in the first entry of the solution /
+ * right-hand side switches M's back-end to LDL^T for good, refactors and solves again.  In LDL^T mode every solve is followed
+ * by iterative refinement on b - M x (M stays intact in HBM) and FAILS if the residual stays above 1e-9 max|b|;
+ * solve_status reports the last relative residual and the refinement steps taken.  symv: y = M x (the dsymv of the reference's
+ * PCG loop, :1446-1588) on the device-resident lower triangle. */
 int  hdsdpcu_kkt_solve(void *kkt, const double *dRhsVec, double *dLhsVec /* NULL: in place */);
+int  hdsdpcu_kkt_solve_status(void *kkt, double *relResidual, int *refineSteps);
+int  hdsdpcu_kkt_symv(void *kkt, const double *x, double *y);
 int  hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *dRhsVec, double *dLhsVec);
 void hdsdpcu_kkt_registerpsdp(void *kkt, int nCones, double **dPrimalX);
 int  hdsdpcu_kkt_getmatrix(void *kkt, double *M /* nRow x nRow column-major, lower meaningful */);

@@ -125,12 +125,20 @@ def test_ill_conditioned_factor_inverse_solve_against_lapack(n, cond):
     be_gpu = np.linalg.norm(A @ x - b) / (nrmA * np.linalg.norm(x))
     be_ref = np.linalg.norm(A @ xr - b) / (nrmA * np.linalg.norm(xr))
     assert be_gpu <= max(20.0 * be_ref, 100 * eps), f"solve backward error {be_gpu:.2e} vs LAPACK {be_ref:.2e}"
-    # triangular solves separately (Lanczos operator)
+    # triangular solves separately (Lanczos operator).  The device multiplies by explicit inverses of the 128 x 128 diagonal leaves
+    # (csrc/trsv.cu); that is forward stable like substitution -- error <= c cond(L) eps relative to the solution (Du Croz & Higham,
+    # "Stability of methods for matrix inversion") -- but not backward stable, so the gate is the FORWARD error against a
+    # long-double substitution, next to LAPACK's own forward error.
+    Lq = Lr.astype(np.longdouble)
+    fq = np.zeros(n, dtype=np.longdouble)
+    bq = b.astype(np.longdouble)
+    for i in range(n):
+        fq[i] = (bq[i] - Lq[i, :i] @ fq[:i]) / Lq[i, i]
     f = ls.fsolve(b)
     fr = sla.solve_triangular(Lr, b, lower=True)
-    bf_gpu = np.linalg.norm(Lr @ f - b) / (np.linalg.norm(Lr, 2) * np.linalg.norm(f))
-    bf_ref = np.linalg.norm(Lr @ fr - b) / (np.linalg.norm(Lr, 2) * np.linalg.norm(fr))
-    assert bf_gpu <= max(50.0 * bf_ref, 1e4 * eps), f"forward-substitution backward error {bf_gpu:.2e} vs LAPACK {bf_ref:.2e}"
+    fe_gpu = float(np.abs(f - fq).max() / np.abs(fq).max())
+    fe_ref = float(np.abs(fr - fq).max() / np.abs(fq).max())
+    assert fe_gpu <= max(50.0 * fe_ref, 100.0 * np.sqrt(cond) * eps), f"forward-substitution forward error {fe_gpu:.2e} vs LAPACK {fe_ref:.2e}"
     # inverse (dpotri twin): residual ||A X - I|| against LAPACK's own
     X = ls.invert()
     Xr = np.linalg.inv(A)
@@ -195,3 +203,82 @@ def test_late_iterate_S_and_M_of_a_real_solve():
     be_ref = np.linalg.norm(Mgf @ xr - b) / (np.linalg.norm(Mgf, 2) * np.linalg.norm(xr))
     assert be_gpu <= max(20.0 * be_ref, 100 * eps), (be_gpu, be_ref, np.linalg.cond(Mfull))
     ref.close(); kkt.close(); cone.close()
+
+
+def test_symv_and_refined_ldl_solve_on_a_late_iterate_M():
+    """The Schur matrix of a real late iterate made indefinite (three eigenvalues pushed below zero, as the reference's
+    "almost indefinite" case): HKKTFactorize switches to LDL^T, every solve is refined on b - M x with the device symv and reports
+    its residual; a NaN right-hand side fails instead of returning garbage.  Also: symv against numpy at m = 3001 (24 x 24 tiles)."""
+    import ctypes
+    sys.path.insert(0, ROOT)
+    from tools import fullsolve
+    from hdsdp_b200 import _lib, api, problem
+    if not os.path.exists(fullsolve.INTEGRATED):
+        pytest.skip("integration/_build/libhdsdp_integrated.so not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        ypath = os.path.join(tmp, "y.npy")
+        res, log, err = fullsolve.run(("theta", 200, 3000), True, 1, max_iter=12, dump_y=ypath)   # a mid-solve iterate: mu ~ 1e-3
+        assert res is not None, log[-2000:] + err[-2000:]
+        y = np.load(ypath)
+    prob = problem.gen_theta(200, 3000, seed=2)
+    m = prob.m
+    sdp, lps, kkt = api.build_problem(prob)
+    cone = sdp[0]
+    cone.set_start(-1e-3)
+    cone.update(1.0, y)
+    assert cone.factorize()
+    kkt.build_up(api.KKT_TYPE_INFEASIBLE)
+    M = np.tril(kkt.get_matrix()); M = M + np.tril(M, -1).T
+    rs = np.random.RandomState(4)
+    x = rs.standard_normal(m)
+    yv = kkt.symv(x)
+    assert np.abs(yv - M @ x).max() <= 1e-13 * np.abs(M).max() * np.abs(x).max() * m ** 0.5
+    lam = np.linalg.eigvalsh(M)
+    shift = 0.5 * (lam[2] + lam[3])
+    kkt.build_up_extra_bound(-shift * np.ones(m), np.zeros(m))
+    assert kkt.factorize() == 0
+    isldl, neg, pert = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    _lib.lib().hdsdpcu_kkt_ldl_status(kkt.h, ctypes.byref(isldl), ctypes.byref(neg), ctypes.byref(pert))
+    assert isldl.value == 1 and neg.value == 3
+    b = rs.standard_normal(m)
+    xs = kkt.solve(b)
+    resid, steps = kkt.solve_status()
+    Ms = M - shift * np.eye(m)
+    true_res = np.abs(Ms @ xs - b).max() / np.abs(b).max()
+    assert resid <= 1e-9 and true_res <= 1e-9, (resid, true_res, steps)
+    xr = np.linalg.solve(Ms, b)
+    assert np.abs(xs - xr).max() <= 1e-6 * np.abs(xr).max() * max(1.0, np.linalg.cond(Ms) * 1e-10)
+    bad = b.copy(); bad[0] = np.nan
+    out = np.zeros(m)
+    rc = _lib.lib().hdsdpcu_kkt_solve(kkt.h, bad.ctypes.data_as(_lib.c_double_p), out.ctypes.data_as(_lib.c_double_p))
+    assert rc == 1, "a NaN right-hand side must fail (HFpLinsysSolve, hdsdp_linsolver.c:2096-2098)"
+    kkt.close(); cone.close()
+
+
+def test_nan_solve_switches_cholesky_backend_to_ldl():
+    """HFpLinsysSolve's rule (hdsdp_linsolver.c:2088-2103): a NaN in rhs[0] -> "KKT system is unstable. Switch to LDL." and the
+    back-end of M stays indefinite from then on."""
+    import ctypes
+    from hdsdp_b200 import _lib, api, problem
+    prob = problem.gen_theta(40, 300, seed=2)
+    sdp, lps, kkt = api.build_problem(prob)
+    c = sdp[0]
+    c.set_start(-2.0)
+    y = 0.05 * np.random.RandomState(0).uniform(-1, 1, prob.m); y[0] = -50.0
+    c.update(1.0, y)
+    assert c.factorize()
+    kkt.build_up(api.KKT_TYPE_INFEASIBLE)
+    assert kkt.factorize() == 0
+    isldl = ctypes.c_int(-1)
+    _lib.lib().hdsdpcu_kkt_ldl_status(kkt.h, ctypes.byref(isldl), None, None)
+    assert isldl.value == 0
+    b = np.ones(prob.m); b[0] = np.nan
+    out = np.zeros(prob.m)
+    rc = _lib.lib().hdsdpcu_kkt_solve(kkt.h, b.ctypes.data_as(_lib.c_double_p), out.ctypes.data_as(_lib.c_double_p))
+    assert rc == 1
+    _lib.lib().hdsdpcu_kkt_ldl_status(kkt.h, ctypes.byref(isldl), None, None)
+    assert isldl.value == 1, "the switch to the indefinite back-end is permanent"
+    M = np.tril(kkt.get_matrix()); M = M + np.tril(M, -1).T
+    x = kkt.solve(np.ones(prob.m))
+    assert np.abs(M @ x - 1.0).max() <= 1e-9
+    kkt.close(); c.close()
