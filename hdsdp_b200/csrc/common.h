@@ -88,6 +88,7 @@ int chol_ldl_prepare(cudaStream_t st, DenseChol *c, int nb, int rank, int nranks
 int hd_num_sms();
 void hd_gemm_set_variant(int v);
 int hd_gemm_get_variant();
+void hd_gemm_set_thin(int max_tiles);
 void hd_chol_set_graph(int on);
 void hd_chol_set_block(int nb);
 void hd_chol_set_leaf(int v);

@@ -244,6 +244,118 @@ __global__ void __launch_bounds__((128 / WM) * (BN / 32) * 32, MINB) dgemm_nt_ke
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Thin products.  One SM delivers ~0.23 TFLOP/s of DMMA, so a 128 x 64 x 256 tile keeps its CTA busy for 18 us: the latency of
+// the small GEMMs on the critical path of the factorisations (leaf triangular solves, 128 / 256-wide syrk and strip updates,
+// chol.cu) is set by the tile size, not by the launch.  This kernel cuts the same products into 32 x 128 tiles (4 x more CTAs,
+// 4 x shorter): 8 warps, warp w owns the 16 columns 16 w .. 16 w + 15 of all 32 rows, 3-stage cp.async pipeline over K chunks
+// of 32.  C may alias A when N == 128 (the in-place leaf solves X <- X Dinv^T): a CTA reads only the rows it later writes.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TH_M = 32, TH_N = 128, TH_K = 32, TH_STAGES = 3, TH_LDA = TH_M + 4, TH_LDB = TH_N + 4, TH_THREADS = 256;
+constexpr int TH_STAGE_DOUBLES = TH_K * (TH_LDA + TH_LDB);
+constexpr int TH_SMEM = TH_STAGES * TH_STAGE_DOUBLES * 8;
+
+__global__ void __launch_bounds__(TH_THREADS, 1) dgemm_nt_thin_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) double smem[];
+    const int m0 = blockIdx.x * TH_M, n0 = blockIdx.y * TH_N;
+    const bool lower = (g.flags & HD_GEMM_LOWER) != 0;
+    if (lower && n0 > m0 + TH_M - 1) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int wn = warp * 16;
+    const int nk = g.K / TH_K;
+    const double *Ag = g.A + m0;
+    const double *Bg = g.B + n0;
+    auto load_stage = [&](int stage, int kt) {
+        double *As = smem + stage * TH_STAGE_DOUBLES;
+        double *Bs = As + TH_K * TH_LDA;
+        const double *a = Ag + (long) kt * TH_K * g.lda;
+        const double *b = Bg + (long) kt * TH_K * g.ldb;
+#pragma unroll
+        for (int i = 0; i < TH_K * (TH_M / 2) / TH_THREADS; ++i) {
+            const int c = tid + i * TH_THREADS, kr = c / (TH_M / 2), mc = (c % (TH_M / 2)) * 2;
+            cp_async16(As + kr * TH_LDA + mc, a + (long) kr * g.lda + mc);
+        }
+#pragma unroll
+        for (int i = 0; i < TH_K * (TH_N / 2) / TH_THREADS; ++i) {
+            const int c = tid + i * TH_THREADS, kr = c / (TH_N / 2), nc = (c % (TH_N / 2)) * 2;
+            cp_async16(Bs + kr * TH_LDB + nc, b + (long) kr * g.ldb + nc);
+        }
+    };
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < TH_STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<TH_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = kt + TH_STAGES - 1;
+            if (nxt < nk) load_stage(nxt % TH_STAGES, nxt);
+            cp_async_commit();
+        }
+        const double *As = smem + (kt % TH_STAGES) * TH_STAGE_DOUBLES;
+        const double *Bs = As + TH_K * TH_LDA;
+#pragma unroll
+        for (int kk = 0; kk < TH_K; kk += 4) {
+            double bf[2], af[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) bf[i] = Bs[(kk + tig) * TH_LDB + wn + 8 * i + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) af[j] = As[(kk + tig) * TH_LDA + 8 * j + gid];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], bf[i], af[j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads(); // in-place products: every warp has finished reading the A rows before any of them is overwritten
+    // thread owns C[m .. m+1][n], n = n0 + wn + 8 i + gid, m = m0 + 8 j + 2 tig
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int n = n0 + wn + 8 * i + gid;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + 8 * j + 2 * tig;
+            if (lower && m + 1 < n) continue;
+            double2 *cp = reinterpret_cast<double2 *>(g.C + (long) n * g.ldc + m);
+            double2 v;
+            if (g.beta == 0.0) {
+                v.x = g.alpha * acc[i][j][0];
+                v.y = g.alpha * acc[i][j][1];
+            } else {
+                const double2 old = *cp;
+                v.x = g.alpha * acc[i][j][0] + g.beta * old.x;
+                v.y = g.alpha * acc[i][j][1] + g.beta * old.y;
+            }
+            if (lower && m < n) g.C[(long) n * g.ldc + m + 1] = v.y;
+            else *cp = v;
+        }
+    }
+}
+
+int g_thin_max_tiles = 96; // products with at most this many 128 x 64 tiles take the thin kernel (0 disables it)
+
+int launch_thin(cudaStream_t st, const GemmArgs &g) {
+    static unsigned long long attr = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr >> (dev & 63) & 1ull)) {
+        HD_CUDA(cudaFuncSetAttribute(dgemm_nt_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TH_SMEM));
+        attr |= 1ull << (dev & 63);
+    }
+    ++g_hd_launches;
+    dgemm_nt_thin_kernel<<<dim3(g.M / TH_M, g.N / TH_N), TH_THREADS, TH_SMEM, st>>>(g);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
 int g_num_sms = 0;
 int g_variant = 4; // 0: 128x128x16 4 stages; 1: 128x128x32 3 stages; 2: 128x64x16 4 stages x2 CTAs; 3: 128x64x32 2 stages x2 CTAs;
                    // 4: as 3 with 8 warps of 32x32 per CTA (16 warps / SM, default); 5: 128x128x32 with 16 warps of 32x32
@@ -287,6 +399,7 @@ int launch_variant(cudaStream_t st, const GemmArgs &g) {
 } // namespace
 
 void hd_gemm_set_variant(int v) { g_variant = v; }
+void hd_gemm_set_thin(int max_tiles) { g_thin_max_tiles = max_tiles; }
 int hd_gemm_get_variant() { return g_variant; }
 
 int hd_num_sms() {
@@ -304,6 +417,16 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
     if (g.M % BM || g.N % BN || g.K % 32) {
         fprintf(stderr, "[hdsdpcu] gemm_nt: unpadded shape %d %d %d\n", g.M, g.N, g.K);
         return HD_FAILED;
+    }
+    // thin products (few tiles): 32 x 128 tiles on 4 x as many SMs; plain alpha / beta / LOWER semantics only
+    if (g_thin_max_tiles > 0 && !g.peerC && !g.ksign && g.bc_nb == 0 && g.B != g.C && (g.A != g.C || g.N == TH_N) &&
+        !(g.flags & (HD_GEMM_KTRI_MAX | HD_GEMM_EPI_HADSQ | HD_GEMM_EPI_COLSCALE))) {
+        long tiles = (long) (g.M / BM) * (g.N / 64);
+        if (g.flags & HD_GEMM_LOWER) tiles = tiles / 2 + g.M / BM;
+        if (tiles <= g_thin_max_tiles) {
+            if ((g.flags & HD_GEMM_LOWER) && g.M != g.N) return HD_FAILED;
+            return launch_thin(st, g);
+        }
     }
     // In-place products (C aliases A, used by the leaf triangular solves with N == 128) are only safe when ONE CTA
     // owns all columns of its row block: the 64-wide tiles would let a sibling CTA overwrite rows still being read.

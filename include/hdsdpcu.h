@@ -42,6 +42,7 @@ int hdsdpcu_debug_leafclk(long long *out);
  *   "gemm_variant" CTA tile / pipeline of the DMMA GEMM: 0 = 128x128x16, 4 stages; 1 = 128x128x32, 3 stages;
  *                  2 = 128x64x16, 4 stages, 2 CTAs/SM; 3 = 128x64x32, 2 stages, 2 CTAs/SM, 4 warps of 64x32;
  *                  4 = as 3 with 8 warps of 32x32 (16 warps/SM, default); 5 = 128x128x32 with 16 warps of 32x32
+ *   "gemm_thin"    products with at most this many 128 x 64 tiles run on the thin-tile kernel (32 x 128 tiles; default 96, 0 = off)
  *   "chol_block"   NB of the blocked look-ahead Cholesky, used when the padded dimension is >= 4 NB
  *                  (-1 = chosen by size, the default; 0 = pure recursion)
  *   "chol_leaf"    128x128 leaf kernel: 1 = column sweep, 2 = DMMA panels (default)

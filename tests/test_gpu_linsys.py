@@ -77,6 +77,27 @@ def test_gemm_nt_matches_numpy():
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max() * K
 
 
+@pytest.mark.parametrize("M,N,K,lower", [(1024, 1024, 256, 0), (1024, 1024, 256, 1), (512, 512, 128, 1), (384, 128, 128, 0), (2048, 256, 512, 0)])
+def test_gemm_nt_tile_paths(M, N, K, lower):
+    """Both tile paths of the DMMA GEMM (thin 32 x 128 tiles below 96 big tiles, 128 x 64 tiles above), full and lower-only."""
+    import torch
+    from hdsdp_b200 import _lib
+    lib = _lib.require_gpu()
+    rs = np.random.RandomState(M + K + lower)
+    A = rs.standard_normal((M, K)); B = rs.standard_normal((N, K)); C = rs.standard_normal((M, N))
+    dA = torch.tensor(A.T.copy(), device="cuda"); dB = torch.tensor(B.T.copy(), device="cuda"); dC = torch.tensor(C.T.copy(), device="cuda")
+    torch.cuda.synchronize()
+    assert lib.hdsdpcu_dgemm_nt_dev(M, N, K, -1.0, dA.data_ptr(), M, dB.data_ptr(), N, 1.0, dC.data_ptr(), M, lower) == 0
+    lib.hdsdpcu_sync()
+    got = dC.cpu().numpy().T
+    ref = C - A @ B.T
+    if lower:
+        iu = np.triu_indices(M, 1)
+        assert np.array_equal(got[iu], C[iu]), "entries strictly above the diagonal must stay untouched"
+        got, ref = np.tril(got), np.tril(ref)
+    assert np.abs(got - ref).max() <= 1e-13 * K * np.abs(ref).max()
+
+
 def test_large_factor_residual():
     """n = 4096: relative residual |A - L L^T| through solves, and log det against numpy."""
     from hdsdp_b200.api import DenseLinsys
