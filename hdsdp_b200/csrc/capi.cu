@@ -93,6 +93,7 @@ int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "gemm_variant") == 0) { hd_gemm_set_variant(value); return HD_OK; }
     if (name && strcmp(name, "gemm_thin") == 0) { hd_gemm_set_thin(value); return HD_OK; }
     if (name && strcmp(name, "chol_block") == 0) { hd_chol_set_block(value); return HD_OK; }
+    if (name && strcmp(name, "chol_sched") == 0) { hd_chol_set_sched(value); return HD_OK; }
     if (name && strcmp(name, "chol_leaf") == 0) { hd_chol_set_leaf(value); return HD_OK; }
     if (name && strcmp(name, "trsv_version") == 0) { hd_trsv_set_version(value); return HD_OK; }
     if (name && strcmp(name, "chol_graph") == 0) { hd_chol_set_graph(value); return HD_OK; }

@@ -567,6 +567,10 @@ int chol_load_dev(cudaStream_t st, DenseChol *c, const double *dS, long lds) {
 //   side :            wait e_col -> potrf(A_{k+1,k+1}) -> A_{k+2..,k+1} <- A L^-T -> e_panel
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_ev_col = nullptr, g_ev_panel = nullptr, g_ev_trail = nullptr;
+// -1: by size (measured on B200, tools/trace_potrf.py); 1: one-step look-ahead with whole panels on the side stream;
+// 2: strip chain + two-step look-ahead (potrf_blocked2); 3: as 2 with the two look-ahead block columns updated by one GEMM
+static int g_sched = -1;
+void hd_chol_set_sched(int v) { g_sched = v; }
 static int g_lookahead_nb = -1; // block size; 0 disables the blocked path; -1 = by size (measured on B200, tools/probe_block.py)
 
 void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
@@ -659,6 +663,108 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
     return HD_OK;
 }
 
+
+// Blocked Cholesky, second schedule (Cholesky mode, single GPU): the critical chain is cut down to what it needs.
+// Diagonal block k+1 depends on panel k only through the NB rows just below diagonal block k, so the high-priority side stream
+// runs  POTRF(k) -> STRIP(k) (solve of those NB rows only) -> DIAGUPD(k+1) (A_{k+1,k+1} -= strip strip^T) -> POTRF(k+1) ...
+// with thin-tile products (gemm_nt.cu), while the main stream does the bulk one to two steps behind:
+//   TRSMB(k)  rows below the strip of panel k           (needs POTRF(k))
+//   UPDCOL(k) block column k+1 below its diagonal block (needs STRIP(k); feeds STRIP(k+1))
+//   UPDCOL2(k) block column k+2 from its diagonal block down (feeds DIAGUPD(k+2): two steps of look-ahead)
+//   UPDREST(k) everything from block column k+3 on (one lower-triangular GEMM, K = NB)
+// The side stream waits for the main stream only when the bulk falls more than one step behind.
+static std::vector<cudaEvent_t> g_evs[4]; // potrf, strip (side -> main); col, col2 (main -> side)
+static cudaEvent_t g_ev_fork = nullptr;
+
+static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
+    if (!g_side) {
+        int lo = 0, hi = 0;
+        HD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        HD_CUDA(cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, hi));
+        HD_CUDA(cudaEventCreateWithFlags(&g_ev_col, cudaEventDisableTiming));
+        HD_CUDA(cudaEventCreateWithFlags(&g_ev_panel, cudaEventDisableTiming));
+    }
+    if (!g_ev_fork) HD_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+    const int nblk = (np + NB - 1) / NB;
+    for (int t = 0; t < 4; ++t)
+        while ((int) g_evs[t].size() < nblk) {
+            cudaEvent_t e;
+            HD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            g_evs[t].push_back(e);
+        }
+    auto start = [&](int k) { return k < nblk ? k * NB : np; };
+    auto size = [&](int k) { return k >= nblk ? 0 : ((k == nblk - 1) ? np - k * NB : NB); };
+    auto leaves = [&](int k) { return dinv + (long) (start(k) / HD_LEAF) * HD_LEAF * HD_LEAF; };
+    auto at = [&](int r, int c) { return A + (long) c * lda + r; };
+    cudaStream_t side = g_side;
+    HD_CUDA(cudaEventRecord(g_ev_fork, st));
+    HD_CUDA(cudaStreamWaitEvent(side, g_ev_fork, 0));
+    for (int k = 0; k < nblk; ++k) {
+        const int s0 = start(k), b0 = size(k), s1 = start(k + 1), b1 = size(k + 1), s2 = start(k + 2), b2 = size(k + 2), s3 = start(k + 3);
+        // ---- side: the chain ----
+        if (k >= 1) {
+            if (k >= 2) HD_CUDA(cudaStreamWaitEvent(side, g_evs[3][k - 2], 0));          // UPDCOL2(k-2) and all earlier bulk updates of A_kk
+            GemmArgs g{};
+            g.M = b0; g.N = b0; g.K = size(k - 1);
+            g.A = at(s0, start(k - 1)); g.lda = lda; g.B = g.A; g.ldb = lda; g.C = at(s0, s0); g.ldc = lda;
+            g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
+            HD_CALL(hd_gemm_nt(side, g));                                                  // DIAGUPD(k)
+        }
+        HD_CALL(potrf_rec(side, at(s0, s0), lda, b0, leaves(k), info, s0));                // POTRF(k)
+        HD_CUDA(cudaEventRecord(g_evs[0][k], side));
+        if (b1 > 0) {
+            if (k >= 1) HD_CUDA(cudaStreamWaitEvent(side, g_evs[2][k - 1], 0));          // UPDCOL(k-1): column block k below its diagonal
+            HD_CALL(trsm_rec(side, at(s1, s0), lda, b1, at(s0, s0), lda, b0, leaves(k)));  // STRIP(k)
+            HD_CUDA(cudaEventRecord(g_evs[1][k], side));
+        }
+        // ---- main: the bulk ----
+        const int rowsR = np - s2;
+        if (b1 > 0 && rowsR > 0) {
+            HD_CUDA(cudaStreamWaitEvent(st, g_evs[0][k], 0));
+            HD_CALL(trsm_rec(st, at(s2, s0), lda, rowsR, at(s0, s0), lda, b0, leaves(k))); // TRSMB(k)
+            HD_CUDA(cudaStreamWaitEvent(st, g_evs[1][k], 0));
+            GemmArgs g{};
+            g.K = b0; g.lda = lda; g.ldb = lda; g.ldc = lda; g.alpha = -1.0; g.beta = 1.0;
+            const int rows3 = np - s3;
+            if (g_sched != 2) {
+                // LOOK(k): block columns k+1 and k+2 from row s2 down as ONE rectangle (the strictly upper part of diagonal
+                // block k+2 receives values nobody reads: the factorisation only ever touches lower triangles of diagonal blocks)
+                g.M = rowsR; g.N = b1 + b2; g.flags = 0;
+                g.A = at(s2, s0); g.B = at(s1, s0); g.C = at(s2, s1);
+                HD_CALL(hd_gemm_nt(st, g));
+                HD_CUDA(cudaEventRecord(g_evs[2][k], st));
+                HD_CUDA(cudaEventRecord(g_evs[3][k], st));
+            } else {
+                g.M = rowsR; g.N = b1; g.flags = 0;
+                g.A = at(s2, s0); g.B = at(s1, s0); g.C = at(s2, s1);
+                HD_CALL(hd_gemm_nt(st, g));                                                    // UPDCOL(k)
+                HD_CUDA(cudaEventRecord(g_evs[2][k], st));
+                g.M = b2; g.N = b2; g.flags = HD_GEMM_LOWER;
+                g.A = at(s2, s0); g.B = at(s2, s0); g.C = at(s2, s2);
+                HD_CALL(hd_gemm_nt(st, g));                                                    // UPDCOL2(k): diagonal block k+2 ...
+                if (rows3 > 0) {
+                    g.M = rows3; g.N = b2; g.flags = 0;
+                    g.A = at(s3, s0); g.B = at(s2, s0); g.C = at(s3, s2);
+                    HD_CALL(hd_gemm_nt(st, g));                                                // ... and the rows below it
+                }
+                HD_CUDA(cudaEventRecord(g_evs[3][k], st));
+            }
+            if (rows3 > 0) {
+                g.M = rows3; g.N = rows3; g.flags = HD_GEMM_LOWER;
+                g.A = at(s3, s0); g.B = at(s3, s0); g.C = at(s3, s3);
+                HD_CALL(hd_gemm_nt(st, g));                                                    // UPDREST(k)
+            }
+        } else if (b1 > 0) {
+            // last panel: nothing below the strip; the events the side stream may wait for still have to exist in stream order
+            HD_CUDA(cudaStreamWaitEvent(st, g_evs[1][k], 0));
+            HD_CUDA(cudaEventRecord(g_evs[2][k], st));
+            HD_CUDA(cudaEventRecord(g_evs[3][k], st));
+        }
+    }
+    HD_CUDA(cudaStreamWaitEvent(st, g_evs[0][nblk - 1], 0)); // join
+    return HD_OK;
+}
+
 namespace {
 __global__ void ldl_floor_kernel(const double *A, long ld, int n, double *floorp, int *nperturb, int nb, int rank, int nranks) {
     __shared__ double red[256];
@@ -707,7 +813,10 @@ static int enqueue_factor(cudaStream_t st, DenseChol *c, int nb) {
         g_ldl = &ctx;
     }
     int rc;
-    if (nb >= HD_LEAF && c->np >= 4 * nb)
+    const int sched = g_sched > 0 ? g_sched : (c->np <= 10240 ? 3 : 1);
+    if (nb >= HD_LEAF && c->np >= 4 * nb && !c->ldl && sched >= 2)
+        rc = potrf_blocked2(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF);
+    else if (nb >= HD_LEAF && c->np >= 4 * nb)
         rc = potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF);
     else
         rc = potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0);
@@ -721,14 +830,16 @@ void hd_chol_set_graph(int on) { g_use_graph = on; }
 int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     HD_CALL(ensure_leaf_attr());
     int nb = g_lookahead_nb;
-    if (nb < 0) nb = c->np < 24000 ? 256 : (c->np < 40000 ? 1024 : 2048);
+    // measured (tools/trace_potrf.py, B200): strip schedule with NB = 128 up to 7k, 256 up to 10k; one-step look-ahead beyond
+    if (nb < 0) nb = c->np <= 7168 ? 128 : (c->np < 14336 ? 256 : (c->np < 24000 ? 512 : (c->np < 40000 ? 1024 : 2048)));
     // Up to n = 6k the factorisation is a launch-bound chain of a few hundred small kernels on two streams whose shapes
     // depend only on (n, block, mode): the second call with the same configuration captures it into a CUDA graph, later
     // calls replay the graph (one launch, dependencies resolved on the device).  The first call runs eagerly so that
     // every lazy allocation / function attribute exists before the capture.  Measured (tools/probe_block.py): -4 % at n = 1500,
     // -3 % at 4096, +2 % at 8192 and beyond (stream priorities are not honoured inside a graph), hence the size limit.
     const unsigned long long key = 1ull | ((unsigned long long) nb << 8) | ((unsigned long long) (c->ldl ? 1 : 0) << 1) |
-                                   ((unsigned long long) g_leaf_version << 2) | ((unsigned long long) hd_gemm_get_variant() << 4);
+                                   ((unsigned long long) g_leaf_version << 2) | ((unsigned long long) hd_gemm_get_variant() << 4) |
+                                   ((unsigned long long) (g_sched + 1) << 40);
     const bool graph_ok = g_use_graph && c->np <= 6144 && getenv("HDSDPCU_TRACE") == nullptr;
     if (graph_ok && c->graph_exec && c->graph_key == key) {
         HD_CUDA(cudaGraphLaunch((cudaGraphExec_t) c->graph_exec, st));

@@ -91,6 +91,7 @@ int hd_gemm_get_variant();
 void hd_gemm_set_thin(int max_tiles);
 void hd_chol_set_graph(int on);
 void hd_chol_set_block(int nb);
+void hd_chol_set_sched(int v);
 void hd_chol_set_leaf(int v);
 void hd_trsv_set_version(int v);
 int hd_leaf_clocks(long long *out);

@@ -45,6 +45,9 @@ int hdsdpcu_debug_leafclk(long long *out);
  *   "gemm_thin"    products with at most this many 128 x 64 tiles run on the thin-tile kernel (32 x 128 tiles; default 96, 0 = off)
  *   "chol_block"   NB of the blocked look-ahead Cholesky, used when the padded dimension is >= 4 NB
  *                  (-1 = chosen by size, the default; 0 = pure recursion)
+ *   "chol_sched"   schedule of the blocked Cholesky: 1 = one step of look-ahead, whole panels on the side stream;
+ *                  2 / 3 = strip chain on the side stream + two steps of look-ahead on the main stream (3: the look-ahead
+ *                  columns as one GEMM); -1 (default) = 3 up to n = 10240, 1 beyond
  *   "chol_leaf"    128x128 leaf kernel: 1 = column sweep, 2 = DMMA panels (default)
  *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default)
  *   "chol_graph"   1 (default): factorisations up to n = 6144 are replayed from a captured CUDA graph from their third call on */
