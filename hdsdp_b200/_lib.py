@@ -88,6 +88,7 @@ _SIGNATURES = {
     "hdsdpcu_kkt_clean": (c_int, [c_void_p, c_int]),
     "hdsdpcu_kkt_buildupextra_bound": (c_int, [c_void_p, c_double_p, c_double_p, c_double_p, c_int]),
     "hdsdpcu_lp_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int_p, c_int_p, c_double_p]),
+    "hdsdpcu_lp_setobjective": (c_int, [c_void_p, c_double_p]),
     "hdsdpcu_lp_destroy": (None, [POINTER(c_void_p)]),
     "hdsdpcu_kkt_buildupextra_lp": (c_int, [c_void_p, c_void_p, c_double_p, c_double, c_int]),
     "hdsdpcu_kkt_regularize": (c_int, [c_void_p, c_double]),

@@ -244,11 +244,13 @@ class LPCone:
         self.dual_residual = 0.0
 
     def slack(self, tau: float, y: np.ndarray) -> np.ndarray:
+        """s = tau c - Rd - A^T y (reference LPConeUpdateImpl, hdsdp_conic_lp.c); O(nnz) host work, vectorised."""
+        if not hasattr(self, "_con"):
+            lo, hi = int(self._beg[1]), int(self._beg[self.m + 1])
+            self._con = np.repeat(np.arange(self.m), np.diff(self._beg[1:self.m + 2]))
+            self._cidx, self._cval = self._idx[lo:hi].astype(np.int64), self._elem[lo:hi]
         s = tau * self.obj - self.dual_residual
-        for k in range(self.m):
-            lo, hi = self._beg[k + 1], self._beg[k + 2]
-            if hi > lo:
-                s[self._idx[lo:hi]] -= y[k] * self._elem[lo:hi]
+        s -= np.bincount(self._cidx, weights=self._cval * np.asarray(y)[self._con], minlength=self.ncol)
         return s
 
     def close(self):

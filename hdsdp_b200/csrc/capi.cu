@@ -20,7 +20,7 @@ struct LinsysCU {
 struct LpCU {
     int m, ncol;
     int *d_colptr, *d_rowidx;
-    double *d_val, *d_sinv;
+    double *d_val, *d_sinv, *d_obj;
 };
 
 int ensure_ready() {
@@ -501,13 +501,25 @@ int hdsdpcu_lp_create(void **plp, int nRow, int nLpCol, const int *beg, const in
     HD_CUDA(cudaMemcpy(lp->d_colptr, ptr.data(), sizeof(int) * (nLpCol + 1), cudaMemcpyHostToDevice));
     HD_CUDA(cudaMemcpy(lp->d_rowidx, rowidx.data(), sizeof(int) * rowidx.size(), cudaMemcpyHostToDevice));
     HD_CUDA(cudaMemcpy(lp->d_val, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice));
+    // objective (column 0 of the user data): needed by the HOMOGENEOUS terms
+    std::vector<double> obj(nLpCol + 1, 0.0);
+    for (int e = beg[0]; e < beg[1]; ++e) obj[idx[e]] = elem[e];
+    HD_CUDA(cudaMalloc(&lp->d_obj, sizeof(double) * (nLpCol + 1)));
+    HD_CUDA(cudaMemcpy(lp->d_obj, obj.data(), sizeof(double) * (nLpCol + 1), cudaMemcpyHostToDevice));
     *plp = lp;
+    return HD_OK;
+}
+int hdsdpcu_lp_setobjective(void *plp, const double *colObj) {
+    // the host solver may rescale the objective after the image was created (LPConeScal, hdsdp_conic_lp.c); ncol doubles
+    LpCU *lp = (LpCU *) plp;
+    HD_CUDA(cudaMemcpyAsync(lp->d_obj, colObj, sizeof(double) * lp->ncol, cudaMemcpyHostToDevice, g_stream));
+    HD_CUDA(cudaStreamSynchronize(g_stream));
     return HD_OK;
 }
 void hdsdpcu_lp_destroy(void **plp) {
     if (!plp || !*plp) return;
     LpCU *lp = (LpCU *) *plp;
-    cudaFree(lp->d_colptr); cudaFree(lp->d_rowidx); cudaFree(lp->d_val); cudaFree(lp->d_sinv);
+    cudaFree(lp->d_colptr); cudaFree(lp->d_rowidx); cudaFree(lp->d_val); cudaFree(lp->d_sinv); cudaFree(lp->d_obj);
     free(lp);
     *plp = nullptr;
 }
@@ -515,13 +527,8 @@ int hdsdpcu_kkt_buildupextra_lp(void *kkt, void *plp, const double *colDualInver
     LpCU *lp = (LpCU *) plp;
     KktCU *k = (KktCU *) kkt;
     if (lp->m != k->m) return HD_FAILED;
-    HD_CALL(kkt_add_lp(k, lp->ncol, lp->d_colptr, lp->d_rowidx, lp->d_val, colDualInverse, lp->d_sinv, dualResidual, typeKKT));
-    if (dualResidual != 0.0) { // dTraceSinv += sum 1/s  (hdsdp_conic_lp.c:276-279)
-        double add[4] = {0, 0, 0, 0};
-        for (int c = 0; c < lp->ncol; ++c) add[3] += colDualInverse[c];
-        HD_CALL(kkt_add_host(k, nullptr, nullptr, nullptr, nullptr, add));
-    }
-    return HD_OK;
+    // M += A D^2 A^T, A s^-1, R_d A s^-2, dTraceSinv and (HOMOGENEOUS) dCSinv, dCSinvCSinv, A C s^-2: all on the device
+    return kkt_add_lp(k, lp->ncol, lp->d_colptr, lp->d_rowidx, lp->d_val, lp->d_obj, colDualInverse, lp->d_sinv, dualResidual, typeKKT);
 }
 int hdsdpcu_kkt_regularize(void *kkt, double reg) { return kkt_regularize((KktCU *) kkt, reg); }
 int hdsdpcu_kkt_export(void *kkt, double *a, double *ard, double *ac, double *cscs, double *cs, double *csrd, double *tr) {

@@ -83,6 +83,35 @@ __global__ void dense_packed_axpy_kernel(const double *__restrict__ P, long npac
     T[col * ldt + row] += s;
 }
 
+// The same sum cut into chunks of matrices (blockIdx.y) when there are thousands of dense coefficients and few packed slots
+// (config E: 3000 matrices x 7260 slots would otherwise run on 29 CTAs): partial sums per chunk, added in chunk order.
+__global__ void dense_packed_axpy_part_kernel(const double *__restrict__ P, long npack, int nds, const int *__restrict__ con,
+                                              const double *__restrict__ coef, int chunk, double *part) {
+    long p = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npack) return;
+    const int d0 = blockIdx.y * chunk, d1 = min(nds, d0 + chunk);
+    double s = 0.0;
+    for (int d = d0; d < d1; ++d) {
+        double c = coef[con[d]];
+        if (c != 0.0) s += c * P[(long) d * npack + p];
+    }
+    part[(long) blockIdx.y * npack + p] = s;
+}
+__global__ void dense_packed_axpy_finish_kernel(const double *__restrict__ part, long npack, int nchunk, int n, long ldt, double *T) {
+    long p = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npack) return;
+    double s = 0.0;
+    for (int q = 0; q < nchunk; ++q) s += part[(long) q * npack + p];
+    double nn = (double) n + 0.5;
+    long col = (long) floor(nn - sqrt(nn * nn - 2.0 * (double) p));
+    if (col < 0) col = 0;
+    if (col > n - 1) col = n - 1;
+    while (col > 0 && col * n - col * (col - 1) / 2 > p) --col;
+    while (col < n - 1 && (col + 1) * n - (col + 1) * col / 2 <= p) ++col;
+    long row = p - (col * n - col * (col - 1) / 2) + col;
+    T[col * ldt + row] += s;
+}
+
 __global__ void scale_columns_kernel(const double *__restrict__ F, double *W, long ld, int rows, int ncols,
                                      const int *__restrict__ con, const double *__restrict__ sign,
                                      const double *__restrict__ coef) {
@@ -490,13 +519,24 @@ __global__ void dd_scatter_kernel(const double *__restrict__ G, long ldg, int nd
     }
 }
 // vec[con_i] += scale * sum_{c,r} U_i[c, r] * X[r, c]   (tr(U_i X)); one thread per constraint, coalesced over i
+// tr(U_i X) for every dense row i; the r-range is cut over blockIdx.y (partial sums in part[y * ndp + i], added in order by
+// dd_trace_finish_kernel) so that a few thousand rows still fill the GPU
 __global__ void dd_trace_kernel(const double *__restrict__ U, int ndp, int nd, int np, int n, const double *__restrict__ X, long ldx,
-                                const int *__restrict__ con, double scale, double *vec) {
+                                double *part) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    const int rchunk = (n + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rchunk, r1 = min(n, r0 + rchunk);
+    double s = 0.0;
+    for (int r = r0; r < r1; ++r)
+        for (int c = 0; c < n; ++c) s += U[i + ((long) c + (long) r * np) * ndp] * X[(long) c * ldx + r];
+    part[(long) blockIdx.y * ndp + i] = s;
+}
+__global__ void dd_trace_finish_kernel(const double *__restrict__ part, int ndp, int nd, int nsplit, const int *__restrict__ con, double scale,
+                                       double *vec) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nd) return;
     double s = 0.0;
-    for (int r = 0; r < n; ++r)
-        for (int c = 0; c < n; ++c) s += U[i + ((long) c + (long) r * np) * ndp] * X[(long) c * ldx + r];
+    for (int q = 0; q < nsplit; ++q) s += part[(long) q * ndp + i];
     vec[con[i]] += scale * s;
 }
 
@@ -735,6 +775,7 @@ void cone_destroy(ConeCU *c) {
     lz_destroy(c->lanczos);
     cudaFree(c->d_prim); cudaFree(c->d_sbv_part); cudaFree(c->d_r_G);
     cudaFree(c->d_dn_vec); cudaFree(c->d_dn_U); cudaFree(c->d_dn_Ut); cudaFree(c->d_dn_G);
+    cudaFree(c->d_dense_part); cudaFree(c->d_dd_part);
     void *ptrs[] = {c->d_pos, c->d_pos_ptr, c->d_ent_con, c->d_ent_val, c->d_dense_packed, c->d_dense_con, c->d_dr1_F,
                     c->d_dr1_W, c->d_dr1_con, c->d_dr1_sign, c->d_coef, c->d_buf[0], c->d_buf[1], c->d_buf[2], c->d_sinv,
                     c->d_scal, c->d_r_con, c->d_r_sign, c->d_r_At, c->d_r_Vt, c->d_r_unit, c->d_r_sp_ptr, c->d_r_sp_idx,
@@ -775,8 +816,20 @@ int cone_update_buffer(ConeCU *c, double cCoef, double aScal, const double *aCoe
                                                                       c->d_coef, c->npos, T);
     }
     if (c->nds > 0) {
-        HDK(dense_packed_axpy_kernel)<<<nblk(c->npack, 256), 256, 0, st>>>(c->d_dense_packed, c->npack, c->nds, c->d_dense_con,
-                                                                       c->d_coef, n, np, T);
+        const long pblocks = nblk(c->npack, 256);
+        int nchunk = (int) ((4L * hd_num_sms() + pblocks - 1) / pblocks);   // ~4 CTAs per SM
+        if (nchunk > c->nds / 16) nchunk = c->nds / 16;
+        if (nchunk >= 2) {
+            const int chunk = (c->nds + nchunk - 1) / nchunk;
+            nchunk = (c->nds + chunk - 1) / chunk;
+            if (!c->d_dense_part) HD_CUDA(cudaMalloc(&c->d_dense_part, sizeof(double) * (size_t) nchunk * c->npack));
+            HDK(dense_packed_axpy_part_kernel)<<<dim3((unsigned) pblocks, nchunk), 256, 0, st>>>(c->d_dense_packed, c->npack, c->nds, c->d_dense_con,
+                                                                                             c->d_coef, chunk, c->d_dense_part);
+            HDK(dense_packed_axpy_finish_kernel)<<<(unsigned) pblocks, 256, 0, st>>>(c->d_dense_part, c->npack, nchunk, n, np, T);
+        } else {
+            HDK(dense_packed_axpy_kernel)<<<nblk(c->npack, 256), 256, 0, st>>>(c->d_dense_packed, c->npack, c->nds, c->d_dense_con,
+                                                                           c->d_coef, n, np, T);
+        }
     }
     if (c->ndr1 > 0) {
         HDK(scale_columns_kernel)<<<nblk((long) np * c->ndr1, 256), 256, 0, st>>>(c->d_dr1_F, c->d_dr1_W, np, np, c->ndr1,
@@ -1035,7 +1088,12 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
     if (dd_batched && (build_matrix || (rd != 0.0 && do_vectors))) {
         HD_CALL(dd_compute_U(c, st));
         if (rd != 0.0 && do_vectors) // tr(Sinv A_i Sinv) = tr(U_i Sinv)
-            HDK(dd_trace_kernel)<<<nblk(c->nd, 128), 128, 0, st>>>(c->d_dn_U, c->ndp, c->nd, np, n, Sinv, np, c->d_dn_con, rd, k->d_asinvrd);
+        {
+            int nsplit = n < 32 ? n : 32;
+            if (!c->d_dd_part) HD_CUDA(cudaMalloc(&c->d_dd_part, sizeof(double) * (size_t) 32 * c->ndp));
+            HDK(dd_trace_kernel)<<<dim3(nblk(c->nd, 128), nsplit), 128, 0, st>>>(c->d_dn_U, c->ndp, c->nd, np, n, Sinv, np, c->d_dd_part);
+            HDK(dd_trace_finish_kernel)<<<nblk(c->nd, 128), 128, 0, st>>>(c->d_dd_part, c->ndp, c->nd, nsplit, c->d_dn_con, rd, k->d_asinvrd);
+        }
     }
     if (c->nd > 0 && rd != 0.0 && !build_matrix && do_vectors && !dd_batched) {
         for (int d = 0; d < c->nd; ++d) {

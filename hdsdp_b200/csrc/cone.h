@@ -51,6 +51,8 @@ struct ConeCU {
     int nds = 0; long npack = 0;
     double *d_dense_packed = nullptr;
     int *d_dense_con = nullptr; // [nds] coefficient index
+    double *d_dense_part = nullptr; // [chunks x npack] partial sums of the chunked packed axpy (many dense coefficients)
+    double *d_dd_part = nullptr;    // [32 x ndp] partial traces of the batched dense rows
     // DSR1 coefficients: factor matrix F [np x nr1dp] (column = a_i), con index, sign
     int ndr1 = 0, ndr1p = 0;
     double *d_dr1_F = nullptr; double *d_dr1_W = nullptr; // W = F diag(coef*sign) workspace
@@ -163,8 +165,8 @@ int kkt_build_up(KktCU *k, int typeKKT);
 int kkt_regularize(KktCU *k, double reg);
 int kkt_add_host(KktCU *k, const double *diagAdd, const double *asinvAdd, const double *asinvrdAdd, const double *asinvcAdd,
                  const double *scalarsAdd4);
-int kkt_add_lp(KktCU *k, int nLpCol, const int *d_colptr, const int *d_rowidx, const double *d_val, const double *sInvHost,
-               double *d_sinv_stage, double rd, int typeKKT);
+int kkt_add_lp(KktCU *k, int nLpCol, const int *d_colptr, const int *d_rowidx, const double *d_val, const double *d_obj,
+               const double *sInvHost, double *d_sinv_stage, double rd, int typeKKT);
 int kkt_export(KktCU *k, double *asinv, double *asinvrd, double *asinvc, double *csinvcsinv, double *csinv, double *csinvrd,
                double *tracesinv);
 int kkt_factorize(KktCU *k, int *info_out);

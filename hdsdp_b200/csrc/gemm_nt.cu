@@ -19,6 +19,8 @@
 // column-major C.  Grid: 1-D, grouped 8x8 super-tiles for L2 reuse of the A/B panels.
 #include "common.h"
 
+int hd_num_sms();
+
 namespace {
 
 constexpr int BM = 128, BN = 128;
@@ -255,9 +257,19 @@ constexpr int TH_M = 32, TH_N = 128, TH_K = 32, TH_STAGES = 3, TH_LDA = TH_M + 4
 constexpr int TH_STAGE_DOUBLES = TH_K * (TH_LDA + TH_LDB);
 constexpr int TH_SMEM = TH_STAGES * TH_STAGE_DOUBLES * 8;
 
-__global__ void __launch_bounds__(TH_THREADS, 1) dgemm_nt_thin_kernel(GemmArgs g) {
+// blockIdx.z > 0 or gridDim.z > 1: split-K.  Slice z covers k in [z * kslice, (z + 1) * kslice) and writes its partial product
+// (alpha = 1, beta = 0) to part + z * M * N (column-major M x N, ld = M); splitk_reduce_kernel then adds the slices in order.
+__global__ void __launch_bounds__(TH_THREADS, 1) dgemm_nt_thin_kernel(GemmArgs g, double *part, int kslice) {
     extern __shared__ __align__(16) double smem[];
     const int m0 = blockIdx.x * TH_M, n0 = blockIdx.y * TH_N;
+    if (part) {
+        g.A += (long) blockIdx.z * kslice * g.lda;
+        g.B += (long) blockIdx.z * kslice * g.ldb;
+        g.K = min(kslice, g.K - (int) blockIdx.z * kslice);
+        g.C = part + (long) blockIdx.z * g.M * g.N;
+        g.ldc = g.M;
+        g.alpha = 1.0; g.beta = 0.0;
+    }
     const bool lower = (g.flags & HD_GEMM_LOWER) != 0;
     if (lower && n0 > m0 + TH_M - 1) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
@@ -340,6 +352,22 @@ __global__ void __launch_bounds__(TH_THREADS, 1) dgemm_nt_thin_kernel(GemmArgs g
     }
 }
 
+// C = alpha * sum_z part_z + beta * C over the (lower part of the) M x N result, slices added in a fixed order (deterministic)
+__global__ void splitk_reduce_kernel(const double *__restrict__ part, int nsplit, int M, int N, double alpha, double beta, double *C,
+                                     long ldc, int lower) {
+    const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long) M * N) return;
+    const int m = (int) (idx % M), n = (int) (idx / M);
+    if (lower && m < n) return;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; ++z) s += part[(long) z * M * N + idx];
+    double *cp = C + (long) n * ldc + m;
+    *cp = (beta == 0.0) ? alpha * s : alpha * s + beta * (*cp);
+}
+
+double *g_splitk_ws = nullptr;
+size_t g_splitk_bytes = 0;
+
 int g_thin_max_tiles = 96; // products with at most this many 128 x 64 tiles take the thin kernel (0 disables it)
 
 int launch_thin(cudaStream_t st, const GemmArgs &g) {
@@ -350,8 +378,36 @@ int launch_thin(cudaStream_t st, const GemmArgs &g) {
         HD_CUDA(cudaFuncSetAttribute(dgemm_nt_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TH_SMEM));
         attr |= 1ull << (dev & 63);
     }
+    // long-K products with a small result (S assembly from thousands of dense rank-one rows: 128 x 128 x 20000) would run on
+    // a handful of CTAs: cut K into slices so that ~2 CTAs per SM are busy, then add the partial products in slice order
+    const long ctas = (long) (g.M / TH_M) * (g.N / TH_N);
+    if (g.K >= 4096 && ctas * 4 <= hd_num_sms() && g.A != g.C) {
+        int nsplit = (int) ((2L * hd_num_sms() + ctas - 1) / ctas);
+        int kslice = ((g.K / nsplit + TH_K - 1) / TH_K) * TH_K;
+        if (kslice < 256) kslice = 256;
+        nsplit = (g.K + kslice - 1) / kslice;
+        const size_t need = sizeof(double) * (size_t) nsplit * g.M * g.N;
+        if (need > g_splitk_bytes) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cap);
+            if (cap == cudaStreamCaptureStatusNone) {
+                if (g_splitk_ws) cudaFree(g_splitk_ws);
+                g_splitk_ws = nullptr; g_splitk_bytes = 0;
+                if (cudaMalloc(&g_splitk_ws, need) == cudaSuccess) g_splitk_bytes = need; else cudaGetLastError();
+            }
+        }
+        if (need <= g_splitk_bytes) {
+            g_hd_launches += 2;
+            dgemm_nt_thin_kernel<<<dim3(g.M / TH_M, g.N / TH_N, nsplit), TH_THREADS, TH_SMEM, st>>>(g, g_splitk_ws, kslice);
+            const long total = (long) g.M * g.N;
+            splitk_reduce_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, st>>>(g_splitk_ws, nsplit, g.M, g.N, g.alpha, g.beta, g.C, g.ldc,
+                                                                                  (g.flags & HD_GEMM_LOWER) ? 1 : 0);
+            HD_CUDA(cudaGetLastError());
+            return HD_OK;
+        }
+    }
     ++g_hd_launches;
-    dgemm_nt_thin_kernel<<<dim3(g.M / TH_M, g.N / TH_N), TH_THREADS, TH_SMEM, st>>>(g);
+    dgemm_nt_thin_kernel<<<dim3(g.M / TH_M, g.N / TH_N), TH_THREADS, TH_SMEM, st>>>(g, nullptr, 0);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
 }

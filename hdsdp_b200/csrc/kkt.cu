@@ -82,25 +82,45 @@ __global__ void scale_vec_kernel(double *x, int m, double a) {
     if (i < m) x[i] *= a;
 }
 
-// LP cone: for LP column c with rows r_0..r_k (CSC by LP column) and weight w_c = s_c^-2:
-//   M[r_a, r_b] += a_a a_b w_c (r_a >= r_b);  asinv[r] += a / s_c ; asinvrd[r] += rd * a * w_c
+// LP cone (reference LPConeGetKKT, interface/hdsdp_conic_lp.c:254-330): for LP column c with rows r_0..r_k (CSC by LP column),
+// weight w_c = s_c^-2:  M[r_a, r_b] += a_a a_b w_c (r_a >= r_b);  asinv[r] += a / s_c ;  asinvrd[r] += rd a w_c ;
+// dTraceSinv += 1 / s_c (rd != 0);  HOMOGENEOUS: dCSinv += c_c / s_c, dCSinvCSinv += (c_c / s_c)^2, asinvc[r] += a c_c w_c
 __global__ void lp_schur_kernel(const int *__restrict__ colptr, const int *__restrict__ rowidx, const double *__restrict__ val,
-                                const double *__restrict__ sinv, int ncol, double rd, int build_matrix, double *M, long ldm,
-                                double *asinv, double *asinvrd) {
+                                const double *__restrict__ sinv, const double *__restrict__ obj, int ncol, double rd, int build_matrix,
+                                int hsd, double *M, long ldm, double *asinv, double *asinvrd, double *asinvc, double *scal) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncol) return;
-    const double si = sinv[c], w = si * si;
-    for (int a = colptr[c]; a < colptr[c + 1]; ++a) {
-        const int ra = rowidx[a];
-        const double va = val[a];
-        atomicAdd(&asinv[ra], va * si);
-        if (rd != 0.0) atomicAdd(&asinvrd[ra], rd * va * w);
-        if (!build_matrix) continue;
-        for (int b = colptr[c]; b <= a; ++b) {
-            const int rb = rowidx[b];
-            const int r = max(ra, rb), q = min(ra, rb);
-            atomicAdd(&M[(long) q * ldm + r], va * val[b] * w);
+    double tr = 0.0, cs = 0.0, cscs = 0.0;
+    if (c < ncol) {
+        const double si = sinv[c], w = si * si;
+        const double oc = hsd ? obj[c] : 0.0;
+        if (rd != 0.0) tr = si;
+        if (hsd) { cs = oc * si; cscs = cs * cs; }
+        for (int a = colptr[c]; a < colptr[c + 1]; ++a) {
+            const int ra = rowidx[a];
+            const double va = val[a];
+            atomicAdd(&asinv[ra], va * si);
+            if (rd != 0.0) atomicAdd(&asinvrd[ra], rd * va * w);
+            if (hsd) atomicAdd(&asinvc[ra], va * oc * w);
+            if (!build_matrix) continue;
+            for (int b = colptr[c]; b <= a; ++b) {
+                const int rb = rowidx[b];
+                const int r = max(ra, rb), q = min(ra, rb);
+                atomicAdd(&M[(long) q * ldm + r], va * val[b] * w);
+            }
         }
+    }
+    // block reduction of the three scalars, one atomic per block
+    __shared__ double red[3][128];
+    red[0][threadIdx.x] = tr; red[1][threadIdx.x] = cs; red[2][threadIdx.x] = cscs;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int q = 0; q < 3; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (rd != 0.0) atomicAdd(&scal[3], red[0][0]);
+        if (hsd) { atomicAdd(&scal[1], red[1][0]); atomicAdd(&scal[0], red[2][0]); }
     }
 }
 
@@ -320,13 +340,14 @@ int kkt_add_host(KktCU *k, const double *diagAdd, const double *asinvAdd, const 
 
 // LP cone twin.  colptr/rowidx/val: CSC by LP column of the [nLpCol x m]^T data (row index = constraint);
 // sInvHost: 1/s per LP column at the current iterate.
-int kkt_add_lp(KktCU *k, int nLpCol, const int *d_colptr, const int *d_rowidx, const double *d_val, const double *sInvHost,
-               double *d_sinv_stage, double rd, int typeKKT) {
+int kkt_add_lp(KktCU *k, int nLpCol, const int *d_colptr, const int *d_rowidx, const double *d_val, const double *d_obj,
+               const double *sInvHost, double *d_sinv_stage, double rd, int typeKKT) {
     cudaStream_t st = hd_stream();
     k->fresh = false;
     HD_CUDA(cudaMemcpyAsync(d_sinv_stage, sInvHost, sizeof(double) * nLpCol, cudaMemcpyHostToDevice, st));
-    HDK(lp_schur_kernel)<<<nblk(nLpCol, 128), 128, 0, st>>>(d_colptr, d_rowidx, d_val, d_sinv_stage, nLpCol, rd,
-                                                        typeKKT != KKT_CORRECTOR, k->d_M, k->mp, k->d_asinv, k->d_asinvrd);
+    HDK(lp_schur_kernel)<<<nblk(nLpCol, 128), 128, 0, st>>>(d_colptr, d_rowidx, d_val, d_sinv_stage, d_obj, nLpCol, rd,
+                                                        typeKKT != KKT_CORRECTOR, typeKKT == KKT_HOMOGENEOUS, k->d_M, k->mp, k->d_asinv,
+                                                        k->d_asinvrd, k->d_asinvc, k->d_scal);
     HD_CUDA(cudaGetLastError());
     HD_CUDA(cudaStreamSynchronize(st));
     return HD_OK;

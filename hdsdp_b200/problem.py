@@ -187,6 +187,18 @@ def gen_maxcut(n: int, degree: int = 6, seed: int = 1) -> Problem:
                    meta={"edges": len(edges)})
 
 
+def gen_maxcut_lp(n: int, degree: int = 4, seed: int = 1, lp_cost: float = 1.0) -> Problem:
+    """Max-cut with one non-negative LP slack per constraint: X_ii + x_i = 1, cost lp_cost * x_i (an SDP cone + an LP cone,
+    strictly feasible on both sides): the smallest well-posed input that drives the LP-cone hooks in a full solve."""
+    base = gen_maxcut(n, degree, seed)
+    cols = [0] * n + list(range(1, n + 1))
+    rows = list(range(n)) + list(range(n))
+    vals = [lp_cost] * n + [1.0] * n
+    beg, idx, elem = _csc_from_triplets(n + 1, cols, rows, vals)
+    return Problem(m=n, cones=[base.cones[0], ConeData("lp", n, beg, idx, elem)], rhs=base.rhs.copy(),
+                   name=f"maxcutlp_n{n}_d{degree}_s{seed}", meta=dict(base.meta))
+
+
 def gen_theta(n: int, nedges: int, seed: int = 2) -> Problem:
     """Config D: Lovasz theta, C = J (all ones), A_1 = I (b_1 = 1), A_k = E_ij for every edge (b_k = 0); m = nedges + 1."""
     rng = random.Random(seed)

@@ -185,6 +185,7 @@ int  hdsdpcu_kkt_buildupextra_bound(void *kkt, const double *diagAdd, const doub
 int  hdsdpcu_kkt_addhost(void *kkt, const double *diagAdd, const double *asinvAdd, const double *asinvRdAdd,
                          const double *asinvCAdd, const double *scalarsAdd4);
 int  hdsdpcu_lp_create(void **plp, int nRow, int nLpCol, const int *matBeg, const int *matIdx, const double *matElem);
+int  hdsdpcu_lp_setobjective(void *lp, const double *colObj);   /* current (possibly rescaled) LP objective, used by the HOMOGENEOUS terms */
 void hdsdpcu_lp_destroy(void **plp);
 int  hdsdpcu_kkt_buildupextra_lp(void *kkt, void *lp, const double *colDualInverse, double dualResidual, int typeKKT);
 int  hdsdpcu_kkt_regularize(void *kkt, double dKKTReg);

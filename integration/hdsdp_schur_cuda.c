@@ -150,7 +150,8 @@ static hdsdp_retcode build_sdp_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, int iCone, i
     return (hdsdp_retcode) hdsdpcu_cone_buildschur(kc->dcone[iCone], iCone, kc->dkkt, typeKKT);
 }
 
-/* LP cone: the O(nnz) slack inversion stays on the host (hdsdp_conic_lp.c:262-271); M += A D^2 A' on the device */
+/* LP cone: the O(nLpCol) slack inversion stays on the host (hdsdp_conic_lp.c:262-271); everything that touches M or the
+   side vectors runs on the device */
 static hdsdp_retcode build_lp_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, int iCone, int typeKKT ) {
     hdsdp_cone_lp *lp = (hdsdp_cone_lp *) HKKT->cones[iCone]->coneData;
     shim_prof_host_begin();
@@ -161,22 +162,11 @@ static hdsdp_retcode build_lp_cone( hdsdp_kkt *HKKT, kkt_cuda *kc, int iCone, in
         for ( int i = 0; i < lp->nCol; ++i ) lp->colDualInverse[i] = 1.0 / lp->colDual[i];
     }
     shim_prof_host_end(SHIM_CAT_SCHUR);
+    /* the reference rescales colObj in place (LPConeScal): hand the current objective to the device image for the HSD terms */
+    if ( typeKKT == KKT_TYPE_HOMOGENEOUS && hdsdpcu_lp_setobjective(kc->dcone[iCone], lp->colObj) != 0 ) return HDSDP_RETCODE_FAILED;
     if ( hdsdpcu_kkt_buildupextra_lp(kc->dkkt, kc->dcone[iCone], lp->colDualInverse, lp->dualResidual, typeKKT) != 0 )
         return HDSDP_RETCODE_FAILED;
-    if ( typeKKT == KKT_TYPE_HOMOGENEOUS ) { /* hdsdp_conic_lp.c:316-327: O(nnz) host arithmetic, added through addhost */
-        double add[4] = {0, 0, 0, 0};
-        shim_prof_host_begin();
-        memset(kc->vecC, 0, sizeof(double) * HKKT->nRow);
-        for ( int i = 0; i < lp->nCol; ++i ) {
-            double cs = lp->colObj[i] * lp->colDualInverse[i];
-            add[1] += cs; add[0] += cs * cs;
-            lp->colBuffer[i] = lp->colObj[i] * lp->colDualInverse[i] * lp->colDualInverse[i];
-        }
-        for ( int r = 0; r < lp->nRow; ++r )
-            for ( int e = lp->rowMatBeg[r]; e < lp->rowMatBeg[r + 1]; ++e ) kc->vecC[r] += lp->rowMatElem[e] * lp->colBuffer[lp->rowMatIdx[e]];
-        shim_prof_host_end(SHIM_CAT_SCHUR);
-        if ( hdsdpcu_kkt_addhost(kc->dkkt, NULL, NULL, NULL, kc->vecC, add) != 0 ) return HDSDP_RETCODE_FAILED;
-    }
+    /* the HOMOGENEOUS terms of hdsdp_conic_lp.c:316-327 (dCSinv, dCSinvCSinv, A C s^-2) are part of the device kernel */
     return HDSDP_RETCODE_OK;
 }
 

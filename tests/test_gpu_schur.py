@@ -76,7 +76,7 @@ def run_point(prob, z, p, sdp, lps, kkt):
         if t != api.KKT_TYPE_CORRECTOR:
             ref_tr = float(z[p + f"{tname}_dTraceSinv"])
             assert abs(got["dTraceSinv"] - ref_tr) <= RTOL * max(abs(ref_tr), 1e-300), f"{tname} dTraceSinv {got['dTraceSinv']} vs {ref_tr}"
-        if t == api.KKT_TYPE_HOMOGENEOUS and not lps:
+        if t == api.KKT_TYPE_HOMOGENEOUS:   # with an LP cone too: its HSD terms are part of the device LP kernel
             ok, msg = close(got["dASinvCSinvVec"], z[p + "hsd_dASinvCSinvVec"])
             assert ok, f"{prob.name} {p} dASinvCSinvVec: {msg}"
             for key in ("dCSinv", "dCSinvCSinv", "dCSinvRdSinv"):
@@ -213,3 +213,50 @@ def test_kkt_switches_to_ldl_when_cholesky_fails():
     assert kkt.factorize() == 0
     x2 = kkt.solve(b)
     assert np.abs(x2 - np.linalg.solve(M, b)).max() <= 1e-9 * np.abs(x2).max()
+
+
+def test_multiblock_midsize_against_oracle():
+    """Config-E shape at a size where the many-row code paths run (split-K S assembly from 5000 dense rank-one rows, chunked packed
+    axpy over 200 dense rows, batched dense x dense Gram block with chunked traces, LP cone), against the pinned plain-C oracle:
+    S per cone 1e-13, Schur matrix / side vectors 1e-10 for the INFEASIBLE and HOMOGENEOUS types."""
+    from hdsdp_b200 import api, problem
+    from oracle import oracle
+    m = 5000
+    prob = problem.gen_multiblock(m, n1=40, n2=30, ndense=200, nlp=300, seed=5)
+    rs = np.random.RandomState(11)
+    y = 1e-3 * rs.uniform(-1, 1, m)
+    tau, rd = 1.0, -2e3
+    sdp, lps, kkt = api.build_problem(prob)
+    ocones = [oracle.OracleCone(c, m) for c in prob.cones if c.kind == "sdp"]
+    for c, oc in zip(sdp, ocones):
+        c.set_start(rd); c.update(tau, y)
+        assert c.factorize()
+        oc.set_resi(rd)
+        ok, _ = oc.set_point(y, tau)
+        assert ok
+        S, So = np.tril(c.get_buffer(api.BUFFER_DUALVAR)), np.tril(oc.get("S"))
+        assert np.abs(S - So).max() <= 1e-13 * np.abs(So).max()
+    lp = lps[0]
+    lp.dual_residual = rd
+    s_lp = lp.slack(tau, y)
+    lpc = [c for c in prob.cones if c.kind == "lp"][0]
+    assert np.abs(s_lp - oracle.lp_slack(lpc, tau, y, rd)).max() <= 1e-12 * np.abs(s_lp).max()
+    for type_kkt in (api.KKT_TYPE_INFEASIBLE, api.KKT_TYPE_HOMOGENEOUS):
+        kkt.build_up(type_kkt)
+        kkt.build_up_extra_lp(lp, 1.0 / s_lp, rd, type_kkt)
+        ok_ = oracle.OracleKKT(m)
+        ok_.clean(type_kkt)
+        for oc in ocones:
+            oc.build_schur(ok_, type_kkt)
+        ok_.add_lp(lpc, s_lp, rd, type_kkt)
+        M, Mo = np.tril(kkt.get_matrix()), np.tril(ok_.M)
+        scale = np.abs(Mo).max()
+        assert (np.abs(M - Mo) <= 1e-10 * np.maximum(np.abs(Mo), 1e-3 * scale)).all(), np.abs(M - Mo).max() / scale
+        v, vo = kkt.export(), ok_.vectors()
+        names = ["dASinvVec", "dASinvRdSinvVec"] + (["dASinvCSinvVec"] if type_kkt == api.KKT_TYPE_HOMOGENEOUS else [])
+        for k in names:
+            sc = np.abs(vo[k]).max()
+            assert (np.abs(v[k] - vo[k]) <= 1e-10 * np.maximum(np.abs(vo[k]), 1e-3 * sc)).all(), (k, np.abs(v[k] - vo[k]).max() / sc)
+    kkt.close()
+    for c in sdp:
+        c.close()

@@ -30,6 +30,8 @@ from oracle import refdrv
 kind, a, b = {spec!r}
 if kind == "maxcut":
     prob = problem.gen_maxcut(a, degree=b, seed=1)
+elif kind == "maxcutlp":
+    prob = problem.gen_maxcut_lp(a, degree=b, seed=1)
 elif kind == "theta":
     prob = problem.gen_theta(a, b, seed=2)
 elif kind == "multiblock":
