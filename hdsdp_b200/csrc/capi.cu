@@ -52,6 +52,7 @@ int hdsdpcu_init(int device) {
         if (const char *e = getenv("HDSDPCU_CHOL_BLOCK")) hd_chol_set_block(atoi(e));
         if (const char *e = getenv("HDSDPCU_CHOL_LEAF")) hd_chol_set_leaf(atoi(e));
         if (const char *e = getenv("HDSDPCU_CHOL_GRAPH")) hd_chol_set_graph(atoi(e));
+        if (const char *e = getenv("HDSDPCU_DIST_DELAY")) hd_dist_set_delay(atoi(e));
     }
     g_ready = true;
     return HD_OK;
@@ -93,6 +94,7 @@ int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "gemm_variant") == 0) { hd_gemm_set_variant(value); return HD_OK; }
     if (name && strcmp(name, "gemm_thin") == 0) { hd_gemm_set_thin(value); return HD_OK; }
     if (name && strcmp(name, "chol_block") == 0) { hd_chol_set_block(value); return HD_OK; }
+    if (name && strcmp(name, "dist_delay") == 0) { hd_dist_set_delay(value); return HD_OK; }
     if (name && strcmp(name, "chol_sched") == 0) { hd_chol_set_sched(value); return HD_OK; }
     if (name && strcmp(name, "chol_leaf") == 0) { hd_chol_set_leaf(value); return HD_OK; }
     if (name && strcmp(name, "trsv_version") == 0) { hd_trsv_set_version(value); return HD_OK; }

@@ -466,7 +466,7 @@ int invert_rec(cudaStream_t st, const double *L, long ldl, int n, const double *
     GemmArgs g{};
     g.M = n1; g.N = n2; g.K = n1;
     g.A = X; g.lda = ldx; g.B = L + n1; g.ldb = ldl; g.C = X + (long) n1 * ldx; g.ldc = ldx;
-    g.alpha = -1.0; g.beta = 0.0; g.flags = 0;
+    g.alpha = -1.0; g.beta = 0.0; g.flags = n1 >= 1024 ? HD_GEMM_KTRI_A : 0; // X11 is upper triangular: half the k-range on average
     HD_CALL(hd_gemm_nt(st, g));
     return trsm_rec(st, X + (long) n1 * ldx, ldx, n1, L + (long) n1 * ldl + n1, ldl, n2, dinv2);
 }

@@ -55,6 +55,7 @@ enum : int {
     HD_GEMM_LOWER = 1,      // only tiles that intersect the lower triangle (m >= n); strict-upper entries untouched
     HD_GEMM_KTRI_MAX = 2,   // operands are "upper triangular in (row,k)": start k at min(m0,n0)... see gemm_nt.cu
     HD_GEMM_EPI_HADSQ = 4,  // epilogue C += sa[m]*sb[n]*acc^2 (rank-one Schur, M2)
+    HD_GEMM_KTRI_A = 16,    // A is upper triangular in (row, k): A[i, k] == 0 for k < i, so the k-range of a tile starts at its first row
     HD_GEMM_EPI_COLSCALE = 8, // beta == 0 only: C[:, n] = alpha * acc * sb[n]   (LDL^T panel solves: X = (A Dinv^T) J)
 };
 
@@ -92,6 +93,7 @@ void hd_gemm_set_thin(int max_tiles);
 void hd_chol_set_graph(int on);
 void hd_chol_set_block(int nb);
 void hd_chol_set_sched(int v);
+void hd_dist_set_delay(int on);
 void hd_chol_set_leaf(int v);
 void hd_trsv_set_version(int v);
 int hd_leaf_clocks(long long *out);

@@ -28,6 +28,9 @@
 #include <cstring>
 #include <vector>
 
+int g_dist_delay = 1; // apply panels in pairs (K = 2 nb) to the block columns that are not next in line
+void hd_dist_set_delay(int on) { g_dist_delay = on; }
+
 namespace {
 
 constexpr int MAXP = 16;
@@ -388,23 +391,49 @@ int dist_factor(DistChol *d, int *info_out, bool ldl) {
             HD_CUDA(cudaEventRecord(R->ev_col, R->st));
             HD_CALL(factor_panel(d, R, k + 1));
         }
-        // (3) everybody: the rest of the owned block columns j > k in one launch
+        // (3) everybody: the rest of the owned block columns.
+        // Delayed updates (Cholesky mode): panels are applied in PAIRS so that the bulk GEMM runs with K = 2 nb (the DMMA GEMM
+        // loses ~6 % at K = 256 against K = 512: the C tile is read-modified-written once per launch).  Even step e: only block
+        // column e+2 receives panel e (its owner needs it before the look-ahead of step e+1); odd step e+1: all owned block
+        // columns j >= e+3 receive panels e and e+1 in one launch.  The look-ahead column of (2) is unaffected.
+        const bool delayed = g_dist_delay && !ldl && nblk >= 4;
         for (int i = 0; i < d->nlocal; ++i) {
             DistRank *R = d->local[i];
-            int j0 = k + 1 + ((R->rank - (k + 1)) % P + P) % P; // first owned block > k
-            if (j0 == k + 1 && R->rank == next) j0 += P;       // already done in (2)
-            if (j0 >= nblk) continue;
             HD_CUDA(cudaSetDevice(R->dev));
-            const int cnt = (nblk - 1 - j0) / P + 1;
-            const int ms = j0 * nb;
-            const double *Pk = R->chol->L + (size_t) s0 * mp;
             GemmArgs g{};
-            g.M = mp - ms; g.N = cnt * nb; g.K = bk;
-            g.A = Pk + ms; g.lda = mp; g.B = Pk + ms; g.ldb = mp; g.C = R->chol->L + (size_t) ms * mp + ms; g.ldc = mp;
-            g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
-            if (ldl) g.ksign = R->chol->sgn + s0;
+            g.lda = mp; g.ldb = mp; g.ldc = mp; g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
             g.bc_nb = nb; g.bc_stride = P * nb;
-            HD_CALL(hd_gemm_nt(R->st, g));
+            if (!delayed) {
+                int j0 = k + 1 + ((R->rank - (k + 1)) % P + P) % P; // first owned block > k
+                if (j0 == k + 1 && R->rank == next) j0 += P;       // already done in (2)
+                if (j0 >= nblk) continue;
+                const int cnt = (nblk - 1 - j0) / P + 1;
+                const int ms = j0 * nb;
+                const double *Pk = R->chol->L + (size_t) s0 * mp;
+                g.M = mp - ms; g.N = cnt * nb; g.K = bk;
+                g.A = Pk + ms; g.B = Pk + ms; g.C = R->chol->L + (size_t) ms * mp + ms;
+                if (ldl) g.ksign = R->chol->sgn + s0;
+                HD_CALL(hd_gemm_nt(R->st, g));
+            } else if (k % 2 == 0) {
+                const int j = k + 2;
+                if (j >= nblk || j % P != R->rank) continue;
+                const int ms = j * nb;
+                const double *Pk = R->chol->L + (size_t) s0 * mp;
+                g.M = mp - ms; g.N = nb; g.K = bk;                  // one owned block column (the last one may be narrower: M = N there)
+                if (j == nblk - 1) g.N = mp - ms;
+                g.A = Pk + ms; g.B = Pk + ms; g.C = R->chol->L + (size_t) ms * mp + ms;
+                HD_CALL(hd_gemm_nt(R->st, g));
+            } else {
+                int j0 = k + 2 + ((R->rank - (k + 2)) % P + P) % P; // first owned block >= k+2
+                if (j0 >= nblk) continue;
+                const int cnt = (nblk - 1 - j0) / P + 1;
+                const int ms = j0 * nb;
+                const int sp = (k - 1) * nb;                        // panels k-1 and k are adjacent block columns of L
+                const double *Pp = R->chol->L + (size_t) sp * mp;
+                g.M = mp - ms; g.N = cnt * nb; g.K = nb + bk;
+                g.A = Pp + ms; g.B = Pp + ms; g.C = R->chol->L + (size_t) ms * mp + ms;
+                HD_CALL(hd_gemm_nt(R->st, g));
+            }
         }
     }
     if (trace) {

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__((128 / WM) * (BN / 32) * 32, MINB) dgemm_nt_ke
 
     int k_lo = 0;
     if (g.flags & HD_GEMM_KTRI_MAX) k_lo = max(m0, n0) & ~(BK - 1); // X[i,k] == 0 for k < i on both operands
+    if (g.flags & HD_GEMM_KTRI_A) k_lo = m0 & ~(BK - 1);            // ... on A only (triangular inverse X11 times a full block)
     const int nk = (g.K - k_lo) / BK;
 
     const double *Ag = g.A + (long) k_lo * g.lda + m0;
@@ -476,7 +477,7 @@ int hd_gemm_nt(cudaStream_t st, const GemmArgs &g) {
     }
     // thin products (few tiles): 32 x 128 tiles on 4 x as many SMs; plain alpha / beta / LOWER semantics only
     if (g_thin_max_tiles > 0 && !g.peerC && !g.ksign && g.bc_nb == 0 && g.B != g.C && (g.A != g.C || g.N == TH_N) &&
-        !(g.flags & (HD_GEMM_KTRI_MAX | HD_GEMM_EPI_HADSQ | HD_GEMM_EPI_COLSCALE))) {
+        !(g.flags & (HD_GEMM_KTRI_MAX | HD_GEMM_KTRI_A | HD_GEMM_EPI_HADSQ | HD_GEMM_EPI_COLSCALE))) {
         long tiles = (long) (g.M / BM) * (g.N / 64);
         if (g.flags & HD_GEMM_LOWER) tiles = tiles / 2 + g.M / BM;
         if (tiles <= g_thin_max_tiles) {

@@ -16,9 +16,13 @@ def spd(n, seed):
     return np.asfortranarray(B @ B.T / n + np.eye(n))
 
 
-@pytest.mark.parametrize("n,nb,P", [(700, 128, 1), (1000, 128, 2), (1500, 256, 3), (2100, 256, 4), (4000, 512, 8), (1300, 512, 2)])
-def test_distributed_schedule_matches_lapack(n, nb, P):
+@pytest.mark.parametrize("delay", [1, 0])
+@pytest.mark.parametrize("n,nb,P", [(700, 128, 1), (1000, 128, 2), (1500, 256, 3), (2100, 256, 4), (4000, 512, 8), (1300, 512, 2),
+                                    (3300, 128, 8), (2900, 256, 2)])
+def test_distributed_schedule_matches_lapack(n, nb, P, delay):
+    """delay = 1: panels applied in pairs (K = 2 nb) to the block columns that are not next in line; 0: every panel at once."""
     lib = _lib.require_gpu()
+    assert lib.hdsdpcu_set_option(b"dist_delay", delay) == 0
     A = spd(n, n + P)
     L0 = np.zeros((n, n), order="F")
     L1 = np.zeros((n, n), order="F")
@@ -31,6 +35,7 @@ def test_distributed_schedule_matches_lapack(n, nb, P):
         got = np.tril(L)
         assert np.isfinite(got).all(), "a rank read a block column it never received"
         assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
+    lib.hdsdpcu_set_option(b"dist_delay", 1)
 
 
 def test_distributed_schedule_reports_indefinite_matrix():
