@@ -48,8 +48,8 @@ int hdsdpcu_debug_leafclk(long long *out);
  *   "chol_sched"   schedule of the blocked Cholesky: 1 = one step of look-ahead, whole panels on the side stream;
  *                  2 / 3 = strip chain on the side stream + two steps of look-ahead on the main stream (3: the look-ahead
  *                  columns as one GEMM); -1 (default) = 3 up to n = 10240, 1 beyond
- *   "dist_delay"   multi-GPU factorisation: 1 (default) = panels are applied in pairs (K = 2 nb) to the block columns that are
- *                  not next in line, 0 = every panel at once (also HDSDPCU_DIST_DELAY)
+ *   "dist_delay"   multi-GPU factorisation: 1 = panels are applied in pairs (K = 2 nb) to the block columns that are not next
+ *                  in line, 0 (default; faster on 8 B200) = every panel at once (also HDSDPCU_DIST_DELAY)
  *   "chol_leaf"    128x128 leaf kernel: 1 = column sweep, 2 = DMMA panels (default)
  *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default)
  *   "chol_graph"   1 (default): factorisations up to n = 6144 are replayed from a captured CUDA graph from their third call on */

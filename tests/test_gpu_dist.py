@@ -35,7 +35,7 @@ def test_distributed_schedule_matches_lapack(n, nb, P, delay):
         got = np.tril(L)
         assert np.isfinite(got).all(), "a rank read a block column it never received"
         assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
-    lib.hdsdpcu_set_option(b"dist_delay", 1)
+    lib.hdsdpcu_set_option(b"dist_delay", 0)
 
 
 def test_distributed_schedule_reports_indefinite_matrix():
