@@ -476,6 +476,33 @@ def measure(hp, dist, args, steps, warmup, with_clocks):
             "fact_s": float(np.mean(hp.fact_ms)) * 1e-3}
 
 
+def measure_pcg(hp, steps):
+    """The same step with the reference's own solver policy for M (Jacobi-PCG first, hdsdp_linsolver.c:1446-1588) on the device:
+    no m^3 factorisation while CG converges.  Reported next to the headline (which is the direct Cholesky the metric names)."""
+    torch, lib = hp.torch, hp.lib
+    hp.kkt.set_solver(1)
+    try:
+        for s in range(2):
+            hp.step_device(s, False)
+        lib.hdsdpcu_sync()
+        e0, e1 = hp.ev(), hp.ev()
+        e0.record(hp.st)
+        for s in range(steps):
+            hp.step_device(2 + s, False)
+        e1.record(hp.st)
+        e1.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / steps
+        st = hp.kkt.pcg_status()
+        stages = hp.stage_times(1)
+        chk = hp.check(None, 0)
+        st_after = hp.kkt.pcg_status()
+    finally:
+        hp.kkt.set_solver(0)
+    return {"value": t, "unit": "s/iteration", "steps": steps, "solver": "Jacobi-PCG on M (reference default policy), device symv",
+            "cg_iterations_last_solve": st["last_iterations"], "cg_solves": st_after["n_solves"], "fallbacks_to_cholesky": st_after["n_fallbacks"],
+            "stages_ms": stages, "check": chk}
+
+
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the UNMODIFIED reference (oracle/_ref) on host cores
 # --------------------------------------------------------------------------------------------------
@@ -630,6 +657,10 @@ def run_ours(args):
     ok = r["check"]["ok"]
     setup_s, gen_s = hp.setup_s, hp.gen_s
     stage_roof = hp.stage_rooflines(r["stages"], peak, hbm)
+    pcg = None
+    if world == 1 and not args.no_pcg:
+        pcg = measure_pcg(hp, args.other_steps)
+        ok = ok and pcg["check"]["ok"]
     hp.close()
 
     # ---- the other BASELINE.json configs as compact records ------------------------------------------
@@ -664,7 +695,7 @@ def run_ours(args):
                        "parallelism": parallelism,
                        "step": "S update + Cholesky(S) + S^-1 + Schur M + regularize + Cholesky(M) + 2 solves", "setup_s": setup_s,
                        "generate_s": gen_s, "check": r["check"], "stages_ms": r["stages"], "stage_roofline": stage_roof,
-                       "other_workloads": others},
+                       "reference_policy_pcg": pcg, "other_workloads": others},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": ncu_traffic("dgemm_nt_kernel"),
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one dgemm_nt launch of the trailing update "
@@ -715,6 +746,7 @@ def main():
     ap.add_argument("--multiblock-m", type=int, default=20000)
     ap.add_argument("--other-steps", type=int, default=5, help="timed steps of the non-headline workloads")
     ap.add_argument("--no-other-workloads", action="store_true")
+    ap.add_argument("--no-pcg", action="store_true", help="skip the reference-policy (Jacobi-PCG) record of the headline workload")
     ap.add_argument("--dist-block", type=int, default=0, help="block-column width of the multi-GPU distribution of M (0 = 512 up to 4 GPUs, 256 beyond)")
     ap.add_argument("--dist-min-m", type=int, default=16000, help="below this m the Schur matrix is replicated instead of distributed over the GPUs")
     ap.add_argument("--ref-big-edges", type=int, default=46000, help="reference arm: theta edges of the one large measurement (m = edges + 1; 0 = skip)")

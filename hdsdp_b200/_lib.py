@@ -96,6 +96,8 @@ _SIGNATURES = {
     "hdsdpcu_kkt_factorize": (c_int, [c_void_p]),
     "hdsdpcu_kkt_solve": (c_int, [c_void_p, c_double_p, c_double_p]),
     "hdsdpcu_kkt_solve_status": (c_int, [c_void_p, c_double_p, c_int_p]),
+    "hdsdpcu_kkt_set_solver": (c_int, [c_void_p, c_int]),
+    "hdsdpcu_kkt_pcg_status": (c_int, [c_void_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "hdsdpcu_kkt_symv": (c_int, [c_void_p, c_double_p, c_double_p]),
     "hdsdpcu_kkt_solve_many": (c_int, [c_void_p, c_int, c_double_p, c_double_p]),
     "hdsdpcu_kkt_registerpsdp": (None, [c_void_p, c_int, POINTER(c_double_p)]),

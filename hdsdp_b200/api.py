@@ -341,6 +341,15 @@ class KKT:
         check(self.lib.hdsdpcu_kkt_symv(self.h, _dp(x), _dp(y)), "symv")
         return y
 
+    def set_solver(self, mode: int):
+        """0: direct Cholesky (default); 1: the reference's policy, Jacobi-PCG first and Cholesky after its first failure."""
+        check(self.lib.hdsdpcu_kkt_set_solver(self.h, int(mode)), "set_solver")
+
+    def pcg_status(self):
+        a, b, c, d = c_int(0), c_int(0), c_int(0), c_int(0)
+        self.lib.hdsdpcu_kkt_pcg_status(self.h, byref(a), byref(b), byref(c), byref(d))
+        return {"use_jacobi": a.value, "last_iterations": b.value, "n_solves": c.value, "n_fallbacks": d.value}
+
     def solve_status(self):
         r = c_double(0.0); s = c_int(0)
         self.lib.hdsdpcu_kkt_solve_status(self.h, byref(r), byref(s))

@@ -557,6 +557,22 @@ int hdsdpcu_kkt_symv(void *kkt, const double *x, double *y) {
     memcpy(y, k->h_vec, sizeof(double) * k->m);
     return HD_OK;
 }
+int hdsdpcu_kkt_set_solver(void *kkt, int mode) {
+    KktCU *k = (KktCU *) kkt;
+    if (mode != 0 && mode != 1) return HD_FAILED;
+    k->solver_mode = mode;
+    k->use_jacobi = true;
+    k->factored = false;
+    return HD_OK;
+}
+int hdsdpcu_kkt_pcg_status(void *kkt, int *useJacobi, int *lastIterations, int *nSolves, int *nFallbacks) {
+    KktCU *k = (KktCU *) kkt;
+    if (useJacobi) *useJacobi = (k->solver_mode == 1 && k->use_jacobi) ? 1 : 0;
+    if (lastIterations) *lastIterations = k->last_cg_iters;
+    if (nSolves) *nSolves = k->cg_solves;
+    if (nFallbacks) *nFallbacks = k->cg_fallbacks;
+    return HD_OK;
+}
 int hdsdpcu_kkt_solve_status(void *kkt, double *relResidual, int *refineSteps) {
     KktCU *k = (KktCU *) kkt;
     if (relResidual) *relResidual = k->last_residual;

@@ -127,6 +127,11 @@ struct KktCU {
     double *d_ref = nullptr;         // [mp x 8] right-hand sides + residuals of the refined LDL^T solves
     double last_residual = 0.0;      // max |b - M x| / max |b| of the last refined solve
     int last_refine_steps = 0;
+    // reference solver policy for M (HDSDP_LINSYS_DENSE_ITERATIVE): 0 = direct Cholesky (default), 1 = Jacobi-PCG first, Cholesky after its first failure
+    int solver_mode = 0;
+    bool use_jacobi = true;
+    double *d_pcg = nullptr;        // [8 x mp + 8] CG vectors and scalars
+    int last_cg_iters = 0, cg_solves = 0, cg_fallbacks = 0;
 };
 
 cudaStream_t hd_stream();

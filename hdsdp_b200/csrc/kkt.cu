@@ -221,6 +221,71 @@ __global__ void vec_add2_kernel(double *x, const double *__restrict__ d, long ld
     if (i < m) for (int v = 0; v < nrhs; ++v) x[(long) v * ld + i] += d[(long) v * ld + i];
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Jacobi-preconditioned conjugate gradients on M: the reference's DEFAULT solver of the Schur system (conjGradSolve,
+// linalg/hdsdp_linsolver.c:1446-1588; HDSDP_LINSYS_DENSE_ITERATIVE, interface/hdsdp_schur.c:19-35), restated with every vector
+// in HBM: one symv_lower_kernel per step (4 m^2 bytes, HBM-bound) plus one single-CTA kernel for the vector updates and dots.
+// scal: 0 r.z  1 d.Md  2 alpha  3 rnew.z  4 ||r||^2  5 beta  6 ||b||^2
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int PCG_T = 1024;
+__device__ __forceinline__ double pcg_block_sum(double v, double *red) {
+    __syncthreads();
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = PCG_T / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    return red[0];
+}
+// x = 0, r = b, d = z = b / jac ; ||b||^2
+__global__ void __launch_bounds__(PCG_T) pcg_init_kernel(const double *__restrict__ b, const double *__restrict__ M, long ld, double *jac, double *x,
+                                                        double *r, double *d, double *z, int m, double *scal) {
+    __shared__ double red[PCG_T];
+    double nb = 0.0;
+    for (int i = threadIdx.x; i < m; i += PCG_T) {
+        const double bi = b[i], ji = M[(long) i * ld + i];
+        jac[i] = ji; x[i] = 0.0; r[i] = bi; d[i] = bi / ji; z[i] = bi / ji;
+        nb += bi * bi;
+    }
+    nb = pcg_block_sum(nb, red);
+    if (threadIdx.x == 0) { scal[6] = nb; scal[4] = nb; }
+}
+// alpha = r.z / d.Md ; x += alpha d ; (full step only) rnew = r - alpha Md ; z = rnew / jac ; beta = rnew.z / r.z ; d = z + beta d
+__global__ void __launch_bounds__(PCG_T) pcg_update_kernel(const double *__restrict__ jac, const double *__restrict__ Md, double *x, double *r,
+                                                          double *d, double *z, int m, int restart, double *scal) {
+    __shared__ double red[PCG_T];
+    double a = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < m; i += PCG_T) { a += z[i] * r[i]; c += d[i] * Md[i]; }
+    const double rz = pcg_block_sum(a, red);
+    const double dMd = pcg_block_sum(c, red);
+    const double alpha = rz / dMd;
+    double e = 0.0, f = 0.0;
+    for (int i = threadIdx.x; i < m; i += PCG_T) {
+        x[i] += alpha * d[i];
+        if (!restart) {
+            const double rn = r[i] - alpha * Md[i];
+            const double zn = rn / jac[i];
+            r[i] = rn; z[i] = zn;
+            e += rn * zn; f += rn * rn;
+        }
+    }
+    if (restart) return;
+    const double rnz = pcg_block_sum(e, red);
+    const double rr = pcg_block_sum(f, red);
+    const double beta = rnz / rz;
+    for (int i = threadIdx.x; i < m; i += PCG_T) d[i] = z[i] + beta * d[i];
+    if (threadIdx.x == 0) { scal[0] = rz; scal[1] = dMd; scal[2] = alpha; scal[3] = rnz; scal[4] = rr; scal[5] = beta; }
+}
+// restart: r = b - t (t = M x) ; d = z = r / jac
+__global__ void __launch_bounds__(PCG_T) pcg_restart_kernel(const double *__restrict__ b, const double *__restrict__ t, const double *__restrict__ jac,
+                                                           double *r, double *d, double *z, int m) {
+    for (int i = threadIdx.x; i < m; i += PCG_T) {
+        const double ri = b[i] - t[i];
+        r[i] = ri; d[i] = ri / jac[i]; z[i] = ri / jac[i];
+    }
+}
+
 inline unsigned nblk(long total, int threads) { return (unsigned) ((total + threads - 1) / threads); }
 
 } // namespace
@@ -264,6 +329,7 @@ void kkt_destroy(KktCU *k) {
     if (k->dist) dist_destroy(k->dist);
     if (k->d_gather) cudaFree(k->d_gather);
     if (k->d_ref) cudaFree(k->d_ref);
+    if (k->d_pcg) cudaFree(k->d_pcg);
     chol_destroy(k->chol);
     delete k;
 }
@@ -377,6 +443,12 @@ int kkt_export(KktCU *k, double *asinv, double *asinvrd, double *asinvc, double 
 // (the reference falls back to dsytrf LDL there, hdsdp_linsolver.c:2036-2039: here the LDL^T mode of chol.cu, see below)
 int kkt_factorize(KktCU *k, int *info_out) {
     cudaStream_t st = hd_stream();
+    if (k->solver_mode == 1 && k->use_jacobi && !(k->dist && k->nranks > 1)) {
+        // conjGradLinSolverNumeric with the Jacobi preconditioner (:1359-1372, :1405-1431): nothing to factor, diag(M) is read by the solve
+        if (info_out) *info_out = 0;
+        k->factored = true;
+        return HD_OK;
+    }
     if (k->dist && k->nranks > 1) {
         // multi-GPU: this rank's block columns of M go into the factor buffer, the peers' columns arrive as factor panels
         HDK(copy_owned_kernel)<<<dim3(k->mp, 8), 256, 0, st>>>(k->chol->L, k->d_M, k->mp, k->mp, k->shard_nb, k->rank, k->nranks);
@@ -431,6 +503,74 @@ int kkt_symv_dev(KktCU *k, const double *d_x, double *d_y, int nRhs) {
     return HD_OK;
 }
 
+
+// The reference's iteration limits and tolerances for the Schur system (HKKTIAllocDenseKKT, interface/hdsdp_schur.c:21-35;
+// defaults of conjGradLinSolverCreate, linalg/hdsdp_linsolver.c:1313-1318)
+static void pcg_params(int m, double *absTol, double *relTol, int *maxIter) {
+    double acc = 1e-12; // KKT_ACCURACY
+    int it = -1;
+    if (m > 20000) { acc *= 100.0; it = 500; }
+    else if (m > 15000) { acc *= 50.0; it = 450; }
+    else if (m > 5000) { acc *= 5.0; it = 120; }
+    *absTol = acc; *relTol = 5.0 * acc;
+    *maxIter = it > 0 ? it : (m / 20 > 50 ? m / 20 : 50);
+}
+
+// conjGradSolve with the Jacobi preconditioner on one device vector (in place).  Returns HD_OK with *converged = 0 when the
+// reference would give up on Jacobi (iteration limit, or iter > 20 with ||r|| > 0.01 ||b||): the caller then switches to Cholesky.
+static int pcg_jacobi_dev(KktCU *k, double *d_x, int *converged) {
+    cudaStream_t st = hd_stream();
+    const int m = k->m, mp = k->mp;
+    if (!k->d_pcg) {
+        HD_CUDA(cudaMalloc(&k->d_pcg, sizeof(double) * ((size_t) 8 * mp + 8)));
+        HD_CUDA(cudaMemset(k->d_pcg, 0, sizeof(double) * ((size_t) 8 * mp + 8)));
+    }
+    double *jac = k->d_pcg, *x = jac + mp, *r = x + mp, *d = r + mp, *z = d + mp, *Md = z + mp, *b = Md + mp, *t = b + mp, *scal = t + mp;
+    double absTol, relTol; int maxIter;
+    pcg_params(m, &absTol, &relTol, &maxIter);
+    HD_CUDA(cudaMemcpyAsync(b, d_x, sizeof(double) * mp, cudaMemcpyDeviceToDevice, st));
+    HDK(pcg_init_kernel)<<<1, PCG_T, 0, st>>>(b, k->d_M, k->mp, jac, x, r, d, z, m, scal);
+    HD_CUDA(cudaMemcpyAsync(k->h_scal + 8, scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    HD_CUDA(cudaStreamSynchronize(st));
+    const double rhsNorm = sqrt(k->h_scal[8 + 6]);
+    double cgTol = absTol < rhsNorm * relTol ? absTol : rhsNorm * relTol;
+    if (cgTol < 0.1 * absTol) cgTol = 0.1 * absTol;
+    *converged = 1;
+    k->last_cg_iters = 0;
+    if (rhsNorm < cgTol) { // the zero vector already qualifies (hdsdp_linsolver.c:1489-1492)
+        HD_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * mp, st));
+        return HD_OK;
+    }
+    HD_CUDA(cudaMemsetAsync(Md, 0, sizeof(double) * mp, st));
+    HD_CALL(kkt_symv_dev(k, d, Md, 1));
+    int iter = 0;
+    bool giveup = false;
+    for (iter = 0; iter < maxIter; ++iter) {
+        const bool restart = (iter % 20 == 5);
+        HDK(pcg_update_kernel)<<<1, PCG_T, 0, st>>>(jac, Md, x, r, d, z, m, restart ? 1 : 0, scal);
+        if (restart) { // r = b - M x from scratch (hdsdp_linsolver.c:1509-1523)
+            HD_CUDA(cudaMemsetAsync(t, 0, sizeof(double) * mp, st));
+            HD_CALL(kkt_symv_dev(k, x, t, 1));
+            HDK(pcg_restart_kernel)<<<1, PCG_T, 0, st>>>(b, t, jac, r, d, z, m);
+            HD_CUDA(cudaMemsetAsync(Md, 0, sizeof(double) * mp, st));
+            HD_CALL(kkt_symv_dev(k, d, Md, 1));
+            continue;
+        }
+        HD_CUDA(cudaMemcpyAsync(k->h_scal + 8, scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+        HD_CUDA(cudaStreamSynchronize(st));
+        const double resiNorm = sqrt(k->h_scal[8 + 4]);
+        if (resiNorm != resiNorm) { giveup = true; break; }           // ITERATIVE_STATUS_NUMERICAL
+        if (iter > 20 && resiNorm > 0.01 * rhsNorm) { giveup = true; break; }
+        if (resiNorm < cgTol) break;
+        HD_CUDA(cudaMemsetAsync(Md, 0, sizeof(double) * mp, st));
+        HD_CALL(kkt_symv_dev(k, d, Md, 1));
+    }
+    k->last_cg_iters = iter;
+    if (giveup || iter >= maxIter) { *converged = 0; return HD_OK; }
+    HD_CUDA(cudaMemcpyAsync(d_x, x, sizeof(double) * mp, cudaMemcpyDeviceToDevice, st));
+    return HD_OK;
+}
+
 static int solve_once(KktCU *k, cudaStream_t st, double *d_x, int nRhs) {
     HD_CALL(chol_fsolve(st, k->chol, d_x, nRhs, k->mp));
     HD_CALL(chol_dsolve(st, k->chol, d_x, nRhs, k->mp));
@@ -444,6 +584,21 @@ static int solve_once(KktCU *k, cudaStream_t st, double *d_x, int nRhs) {
 int kkt_solve_dev(KktCU *k, double *d_x, int nRhs) {
     if (!k->factored) return HD_FAILED;
     cudaStream_t st = hd_stream();
+    if (k->solver_mode == 1 && k->use_jacobi && !(k->dist && k->nranks > 1)) {
+        // reference policy: Jacobi-PCG on M; the first failure switches to the Cholesky factor for good (:1558-1567)
+        for (int v = 0; v < nRhs; ++v) {
+            int ok = 0;
+            HD_CALL(pcg_jacobi_dev(k, d_x + (size_t) v * k->mp, &ok));
+            k->cg_solves += 1;
+            if (!ok) {
+                k->use_jacobi = false;
+                k->cg_fallbacks += 1;
+                HD_CALL(kkt_factorize(k, nullptr));     // M is intact: factor it now, then solve the remaining vectors directly
+                return kkt_solve_dev(k, d_x + (size_t) v * k->mp, nRhs - v);
+            }
+        }
+        return HD_OK;
+    }
     const bool refine = k->chol->ldl && !(k->dist && k->nranks > 1);
     if (!refine) return solve_once(k, st, d_x, nRhs);
     if (nRhs > 4) { // the refinement workspace holds 4 right-hand sides

@@ -202,6 +202,14 @@ int  hdsdpcu_kkt_ldl_status(void *kkt, int *isLdl, int *nNegative, int *nPerturb
  * PCG loop, :1446-1588) on the device-resident lower triangle. */
 int  hdsdpcu_kkt_solve(void *kkt, const double *dRhsVec, double *dLhsVec /* NULL: in place */);
 int  hdsdpcu_kkt_solve_status(void *kkt, double *relResidual, int *refineSteps);
+/* Solver policy for M.  0 (default): direct Cholesky, as the north star asks.  1: the reference's own default policy
+ * (HDSDP_LINSYS_DENSE_ITERATIVE, conjGradSolve linalg/hdsdp_linsolver.c:1446-1588 with the limits of interface/hdsdp_schur.c:21-35):
+ * factorize only records diag(M); solve runs Jacobi-preconditioned CG with every vector in HBM (one symv over the lower triangle
+ * per step); the first solve that hits the iteration limit or stalls (iter > 20 and ||r|| > 0.01 ||b||) factors M by Cholesky and
+ * every later solve is direct (sticky, as the reference's useJacobi = 0).  Single GPU only.  pcg_status: still on Jacobi?, CG
+ * steps of the last solve, number of CG solves, number of fallbacks. */
+int  hdsdpcu_kkt_set_solver(void *kkt, int mode);
+int  hdsdpcu_kkt_pcg_status(void *kkt, int *useJacobi, int *lastIterations, int *nSolves, int *nFallbacks);
 int  hdsdpcu_kkt_symv(void *kkt, const double *x, double *y);
 int  hdsdpcu_kkt_solve_many(void *kkt, int nRhs, const double *dRhsVec, double *dLhsVec);
 void hdsdpcu_kkt_registerpsdp(void *kkt, int nCones, double **dPrimalX);

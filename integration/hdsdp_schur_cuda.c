@@ -121,6 +121,10 @@ extern hdsdp_retcode HKKTInit( hdsdp_kkt *HKKT, int nRow, int nCones, hdsdp_cone
     }
     int drc = hdsdpcu_kkt_create(&kc->dkkt, nRow);
     if ( drc != 0 ) return drc == 2 ? HDSDP_RETCODE_MEMORY : HDSDP_RETCODE_FAILED;
+    /* HDSDPCU_KKT_SOLVER=pcg: the reference's own policy for M (hdsdp_schur.c:19-35: Jacobi-PCG first, Cholesky after its first
+       failure) on the device instead of the direct Cholesky factorisation */
+    const char *solver = getenv("HDSDPCU_KKT_SOLVER");
+    if ( solver && strcmp(solver, "pcg") == 0 && hdsdpcu_kkt_set_solver(kc->dkkt, 1) != 0 ) return HDSDP_RETCODE_FAILED;
     for ( int iCone = 0; iCone < nCones; ++iCone ) {
         hdsdp_cone *c = cones[iCone];
         user_data *u = (user_data *) c->usrData;

@@ -304,3 +304,43 @@ def test_nan_solve_switches_cholesky_backend_to_ldl():
     x = kkt.solve(np.ones(prob.m))
     assert np.abs(M @ x - 1.0).max() <= 1e-9
     kkt.close(); c.close()
+
+
+def test_reference_pcg_policy_on_device():
+    """hdsdpcu_kkt_set_solver(1): the reference's default solver of M (Jacobi-PCG, conjGradSolve) with the vectors in HBM must give
+    the direct solve's answer to the reference's own tolerance, report its iteration count, and fall back to Cholesky (sticky) when
+    CG cannot converge -- here on theta n = 200, m = 3001 at bench.py's iterate and at an ill-conditioned late iterate."""
+    import bench
+    from hdsdp_b200 import api, problem
+    prob = problem.gen_theta(200, 3000, seed=2)
+    m = prob.m
+    sdp, lps, kkt = api.build_problem(prob)
+    cone = sdp[0]
+    cone.set_start(bench.RD)
+    y = bench.theta_point(m, 200, 0)
+    cone.update(bench.TAU, y)
+    assert cone.factorize()
+    kkt.build_up(api.KKT_TYPE_INFEASIBLE)
+    kkt.regularize(bench.KKT_REG)
+    assert kkt.factorize() == 0
+    b = prob.rhs + 0.1 * np.random.RandomState(1).standard_normal(m)
+    x_direct = kkt.solve(b)
+    kkt.set_solver(1)
+    assert kkt.factorize() == 0           # Numeric of the iterative back-end: nothing to factor
+    x_cg = kkt.solve(b)
+    st = kkt.pcg_status()
+    assert st["use_jacobi"] == 1 and 1 <= st["last_iterations"] <= 120 and st["n_fallbacks"] == 0, st
+    M = np.tril(kkt.get_matrix()); M = M + np.tril(M, -1).T
+    assert np.linalg.norm(M @ x_cg - b) <= 1e-10, np.linalg.norm(M @ x_cg - b)      # cgTol = min(absTol, relTol ||b||) <= 1e-12
+    assert np.abs(x_cg - x_direct).max() <= 1e-8 * np.abs(x_direct).max()
+    # a system Jacobi-CG cannot solve within the reference's limits: pushed towards singularity
+    lam = np.linalg.eigvalsh(M)
+    kkt.build_up_extra_bound(-(lam[0] * (1.0 - 1e-9)) * np.ones(m), np.zeros(m))
+    assert kkt.factorize() == 0
+    x2 = kkt.solve(b)
+    st = kkt.pcg_status()
+    assert st["use_jacobi"] == 0 and st["n_fallbacks"] == 1, st                       # sticky switch to the Cholesky factor
+    M2 = M - lam[0] * (1.0 - 1e-9) * np.eye(m)
+    assert np.linalg.norm(M2 @ x2 - b) <= 1e-6 * np.linalg.norm(b) * np.linalg.cond(M2) * 1e-10 + 1e-6
+    kkt.set_solver(0)
+    kkt.close(); cone.close()
