@@ -123,3 +123,56 @@ def test_binary_container_roundtrip(tmp_path):
         f.write(b"X")
     with pytest.raises(ValueError):
         problem.load_bin(path)
+
+
+def test_bench_operator_checker_against_the_oracle():
+    """bench.py's correctness check (config.check) applies the operator form of M with numpy; here the checker itself is checked
+    against the oracle's explicit Schur matrix on small theta / max-cut / multi-block (+LP) problems."""
+    import bench
+    from hdsdp_b200 import problem
+    from oracle import oracle
+    rs = np.random.RandomState(0)
+    for prob, rd, y in ((problem.gen_theta(30, 80, seed=2), -1.0, None), (problem.gen_maxcut(40, degree=4, seed=1), -10.0, None),
+                        (problem.gen_multiblock(50, n1=8, n2=6, ndense=10, nlp=12, seed=3), -1e3, "zero")):
+        m = prob.m
+        if y is None:
+            y = bench.theta_point(m, 30, 0) if "theta" in prob.name else bench.maxcut_point(m, 40, 0)
+        else:
+            y = np.zeros(m)
+        ok_ = oracle.OracleKKT(m)
+        ok_.clean(0)
+        sinvs = []
+        for cone in prob.cones:
+            if cone.kind != "sdp":
+                continue
+            oc = oracle.OracleCone(cone, m)
+            oc.set_resi(rd)
+            ok, _ = oc.set_point(y, 1.0)
+            assert ok
+            oc.build_schur(ok_, 0)
+            S = oc.get("S"); S = np.tril(S) + np.tril(S, -1).T
+            sinvs.append(np.linalg.inv(S))
+        lp_d2 = None
+        for cone in prob.cones:
+            if cone.kind == "lp":
+                s = oracle.lp_slack(cone, 1.0, y, rd)
+                ok_.add_lp(cone, s, rd, 0)
+                lp_d2 = (1.0 / s) ** 2
+        M = np.tril(ok_.M) + np.tril(ok_.M, -1).T
+        x = rs.standard_normal(m)
+        got = bench.apply_schur_operator(prob, sinvs, x, lp_d2=lp_d2)
+        assert np.abs(got - M @ x).max() <= 1e-10 * np.abs(M @ x).max(), prob.name
+
+
+def test_integration_hooks_are_linked_in():
+    """The drop-in build must carry the three hooks: the reference's HConeSetData / HFpLinsysCreate renamed, ours in their place."""
+    lib = os.path.join(ROOT, "integration", "_build", "libhdsdp_integrated.so")
+    if not os.path.exists(lib):
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", lib], text=True)
+    for name in ("HConeSetData", "HConeSetData_ref", "HFpLinsysCreate", "HFpLinsysCreate_ref", "HKKTBuildUp", "fds_syev_dimacs",
+                 "hdsdpcu_shim_cone_handle", "shim_prof_report"):
+        assert re.search(rf"\b[TtDB] {name}\b", syms), f"{name} missing from libhdsdp_integrated.so"
+    und = subprocess.check_output(["nm", "-D", "--undefined-only", lib], text=True)
+    for name in ("hdsdpcu_cone_update", "hdsdpcu_cone_ratiotest", "hdsdpcu_kkt_factorize", "hdsdpcu_cone_getprimal", "hdsdpcu_sym_extreme_eig"):
+        assert name in und, f"the drop-in does not call {name}"
