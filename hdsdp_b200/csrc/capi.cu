@@ -44,7 +44,17 @@ int hdsdpcu_init(int device) {
         fprintf(stderr, "[hdsdpcu] no CUDA device: the hot path has no CPU fallback\n");
         return HD_FAILED;
     }
-    if (device >= 0) HD_CUDA(cudaSetDevice(device));
+    // one device per process (one process per GPU is the multi-GPU model): the library stream, the side
+    // stream of the factorisations and their events belong to the first device selected
+    static int g_device = -1;
+    if (device >= 0) {
+        if (g_device >= 0 && device != g_device) {
+            fprintf(stderr, "[hdsdpcu] hdsdpcu_init(%d): this process is already bound to device %d (one process per GPU)\n", device, g_device);
+            return HD_FAILED;
+        }
+        HD_CUDA(cudaSetDevice(device));
+    }
+    if (g_device < 0) HD_CUDA(cudaGetDevice(&g_device));
     if (!g_stream) HD_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     if (!g_ready) {
         // measurement knobs can also come from the environment (HDSDPCU_GEMM_VARIANT, HDSDPCU_CHOL_BLOCK, HDSDPCU_CHOL_LEAF)

@@ -106,8 +106,14 @@ __device__ __forceinline__ void dmma_tile(double &c0, double &c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
+// phase clocks of the leaf (tools/leafclk.py): compiled in only with -DHDSDPCU_LEAFCLK (stores into one global array would
+// race between leaves running concurrently on the main and side streams and add traffic to the latency-critical kernel)
 __device__ long long g_leaf_clk[40];
+#ifdef HDSDPCU_LEAFCLK
 #define LEAF_CLK(i) do { if (tid == 0) g_leaf_clk[i] = clock64(); } while (0)
+#else
+#define LEAF_CLK(i) do { } while (0)
+#endif
 
 // LDL = true: signed Cholesky A = L J L^T with J = diag(+-1) (unpivoted LDL^T with D = J, the scale folded into L);
 // pivots with |d| <= *floorp are replaced by +floorp (static pivoting) and counted.  sgn[j] receives J_jj.
@@ -825,7 +831,8 @@ static int enqueue_factor(cudaStream_t st, DenseChol *c, int nb) {
 }
 
 static int g_use_graph = 1;
-void hd_chol_set_graph(int on) { g_use_graph = on; }
+static int g_graph_max = 6144;
+void hd_chol_set_graph(int on) { g_use_graph = on != 0; if (on > 1) g_graph_max = on; }
 
 int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     HD_CALL(ensure_leaf_attr());
@@ -840,7 +847,7 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     const unsigned long long key = 1ull | ((unsigned long long) nb << 8) | ((unsigned long long) (c->ldl ? 1 : 0) << 1) |
                                    ((unsigned long long) g_leaf_version << 2) | ((unsigned long long) hd_gemm_get_variant() << 4) |
                                    ((unsigned long long) (g_sched + 1) << 40);
-    const bool graph_ok = g_use_graph && c->np <= 6144 && getenv("HDSDPCU_TRACE") == nullptr;
+    const bool graph_ok = g_use_graph && c->np <= g_graph_max && getenv("HDSDPCU_TRACE") == nullptr;
     if (graph_ok && c->graph_exec && c->graph_key == key) {
         HD_CUDA(cudaGraphLaunch((cudaGraphExec_t) c->graph_exec, st));
         g_hd_launches += c->graph_kernels; // the kernels inside the replayed graph

@@ -550,6 +550,10 @@ bool g_ss_attr = false;
 // creation
 // =================================================================================================
 int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx, const double *elem) {
+    if (hd_pad(nCol) > 46340) { // linear positions row + col * np are 32-bit (as the reference's own int indices)
+        fprintf(stderr, "[hdsdpcu] cone_create: cone dimension %d is above the 32-bit index range of the dense dual matrix (46340)\n", nCol);
+        return HD_FAILED;
+    }
     ConeCU *c = new ConeCU();
     c->m = nRow; c->n = nCol; c->np = hd_pad(nCol);
     const int m = nRow, n = nCol, np = c->np;

@@ -35,7 +35,8 @@ int hdsdpcu_timer_start(void);
 int hdsdpcu_timer_stop(double *ms);
 /* device-to-device copy on the library stream (bench plumbing for HBM-resident inputs) */
 int hdsdpcu_copy_dev(void *d_dst, const void *d_src, long bytes);
-/* debug: clock64() stamps of the phases of the last leaf factorisation (40 values, tools/leafclk.py) */
+/* debug: clock64() stamps of the phases of the last leaf factorisation (40 values, tools/leafclk.py); only filled when the
+ * library is built with -DHDSDPCU_LEAFCLK */
 int hdsdpcu_debug_leafclk(long long *out);
 /* tuning knobs for measurements (also settable through the environment as HDSDPCU_GEMM_VARIANT / HDSDPCU_CHOL_BLOCK /
  * HDSDPCU_CHOL_LEAF before hdsdpcu_init):
