@@ -125,70 +125,74 @@ __global__ void lp_schur_kernel(const int *__restrict__ colptr, const int *__res
 }
 
 // y += M x for a symmetric M of which only the lower triangle is stored (the dsymv('L') of the reference's PCG loop,
-// linalg/hdsdp_linsolver.c:1446-1588), nrhs <= 2 vectors.  HBM-bound: every 128 x 128 tile of the lower triangle is read ONCE
-// (4 m^2 bytes) and used for both y_i += T x_j and y_j += T^T x_i.  One CTA (256 threads) per tile: thread (row, half) holds
-// 64 entries of its tile row in registers (coalesced loads, all in flight together); the row product is reduced over the two
-// halves through shared memory, the column products over the 32 lanes by shuffles and over the 4 warps of a half through
-// shared memory; results are added to y with atomics.
+// linalg/hdsdp_linsolver.c:1446-1588), nrhs <= 2 vectors.  HBM-bound: every entry of the lower triangle is read ONCE (4 m^2 bytes)
+// and used for both y_i += T x_j and y_j += T^T x_i.  One CTA (256 threads, two per SM so that one CTA's loads overlap the other's
+// reductions) per 128 x 64 half-tile: thread (row, half) holds 32 entries of its tile row in registers (coalesced loads, all in
+// flight together); the row product is reduced over the two halves through shared memory, the column products over the 32
+// lanes by shuffles and over the 4 warps of a half through shared memory; results are added to y with atomics.
+constexpr int SV_N = 64;
 template <int NRHS>
-__global__ void __launch_bounds__(256) symv_lower_kernel(const double *__restrict__ M, long ld, int nblk, const double *__restrict__ x,
-                                                        long ldx, double *y, long ldy) {
-    __shared__ double xi[NRHS][HD_LEAF], xj[NRHS][HD_LEAF];
+__global__ void __launch_bounds__(256, 2) symv_lower_kernel(const double *__restrict__ M, long ld, int nblk, const double *__restrict__ x,
+                                                           long ldx, double *y, long ldy) {
+    __shared__ double xi[NRHS][HD_LEAF], xj[NRHS][SV_N];
     __shared__ double rowred[NRHS][2][HD_LEAF];
-    __shared__ double colred[NRHS][4][HD_LEAF];
-    // tile (i, j), i >= j, from the linear index: i = floor((sqrt(8 b + 1) - 1) / 2)
+    __shared__ double colred[NRHS][4][SV_N];
+    // half-tile (i, j2): row block i, 64-column block j2 <= 2 i + 1; row block i owns 2 (i + 1) of them: i = floor((sqrt(4 b + 1) - 1) / 2)
     const long b = blockIdx.x;
-    int i = (int) ((sqrt(8.0 * (double) b + 1.0) - 1.0) * 0.5);
-    while ((long) (i + 1) * (i + 2) / 2 <= b) ++i;
-    while ((long) i * (i + 1) / 2 > b) --i;
-    const int j = (int) (b - (long) i * (i + 1) / 2);
+    int i = (int) ((sqrt(4.0 * (double) b + 1.0) - 1.0) * 0.5);
+    while ((long) (i + 1) * (i + 2) <= b) ++i;
+    while ((long) i * (i + 1) > b) --i;
+    const int j2 = (int) (b - (long) i * (i + 1));
     if (i >= nblk) return;
     const int t = threadIdx.x, row = t & 127, half = t >> 7, lane = t & 31, w4 = (t >> 5) & 3;
-    const bool diag = (i == j);
-    const double *T = M + ((long) j * HD_LEAF + half * 64) * ld + (long) i * HD_LEAF + row;
-    double tl[64];
+    const bool diag = (j2 >> 1) == i;
+    const int c0 = (j2 & 1) * SV_N;                 // first column of this half-tile inside its leaf
+    const double *T = M + ((long) j2 * SV_N + half * 32) * ld + (long) i * HD_LEAF + row;
+    double tl[32];
 #pragma unroll
-    for (int q = 0; q < 64; ++q) tl[q] = __ldcs(&T[(long) q * ld]);
+    for (int q = 0; q < 32; ++q) tl[q] = __ldcs(&T[(long) q * ld]);
     if (t < HD_LEAF) {
 #pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            xi[r][t] = x[(long) r * ldx + (long) i * HD_LEAF + t];
-            xj[r][t] = x[(long) r * ldx + (long) j * HD_LEAF + t];
-        }
-    }
-    if (diag) { // only the lower triangle of a diagonal tile is data
+        for (int r = 0; r < NRHS; ++r) xi[r][t] = x[(long) r * ldx + (long) i * HD_LEAF + t];
+    } else if (t < HD_LEAF + SV_N) {
 #pragma unroll
-        for (int q = 0; q < 64; ++q) if (half * 64 + q > row) tl[q] = 0.0;
+        for (int r = 0; r < NRHS; ++r) xj[r][t - HD_LEAF] = x[(long) r * ldx + (long) j2 * SV_N + (t - HD_LEAF)];
+    }
+    if (diag) { // only the lower triangle of a diagonal leaf is data
+#pragma unroll
+        for (int q = 0; q < 32; ++q) if (c0 + half * 32 + q > row) tl[q] = 0.0;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) {
         double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < 64; ++q) acc += tl[q] * xj[r][half * 64 + q];
+        for (int q = 0; q < 32; ++q) acc += tl[q] * xj[r][half * 32 + q];
         rowred[r][half][row] = acc;
     }
-    // transposed part: column c = half*64 + q gets sum_row T[row, c] x_i[row]; on a diagonal tile the diagonal itself
-    // was already used by the row product
+    // transposed part: column c = half*32 + q gets sum_row T[row, c] x_i[row]; on a diagonal leaf the diagonal itself was
+    // already used by the row product
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) {
         const double xv = xi[r][row];
 #pragma unroll
-        for (int q = 0; q < 64; ++q) {
+        for (int q = 0; q < 32; ++q) {
             double v = tl[q] * xv;
-            if (diag && half * 64 + q == row) v = 0.0;
+            if (diag && c0 + half * 32 + q == row) v = 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == (q & 31)) colred[r][w4][half * 64 + q] = v;
+            if (lane == q) colred[r][w4][half * 32 + q] = v;
         }
     }
     __syncthreads();
     if (t < HD_LEAF) {
 #pragma unroll
-        for (int r = 0; r < NRHS; ++r) {
-            atomicAdd(&y[(long) r * ldy + (long) i * HD_LEAF + t], rowred[r][0][t] + rowred[r][1][t]);
-            atomicAdd(&y[(long) r * ldy + (long) j * HD_LEAF + t], colred[r][0][t] + colred[r][1][t] + colred[r][2][t] + colred[r][3][t]);
-        }
+        for (int r = 0; r < NRHS; ++r) atomicAdd(&y[(long) r * ldy + (long) i * HD_LEAF + t], rowred[r][0][t] + rowred[r][1][t]);
+    } else if (t < HD_LEAF + SV_N) {
+        const int c = t - HD_LEAF;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r)
+            atomicAdd(&y[(long) r * ldy + (long) j2 * SV_N + c], colred[r][0][c] + colred[r][1][c] + colred[r][2][c] + colred[r][3][c]);
     }
 }
 
@@ -492,7 +496,7 @@ int kkt_symv_dev(KktCU *k, const double *d_x, double *d_y, int nRhs) {
     if (k->dist && k->nranks > 1) return HD_FAILED; // every rank holds only its own block columns of M
     cudaStream_t st = hd_stream();
     const int nb = k->mp / HD_LEAF;
-    const long tiles = (long) nb * (nb + 1) / 2;
+    const long tiles = (long) nb * (nb + 1);   // 128 x 64 half-tiles of the lower triangle
     for (int r0 = 0; r0 < nRhs; r0 += 2) {
         const int nr = (nRhs - r0 >= 2) ? 2 : 1;
         ++g_hd_launches;
