@@ -145,51 +145,86 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base, doubl
     }
     __syncthreads();
     LEAF_CLK(1);
-    for (int p = 0; p < 8; ++p) {
-        const int c0 = 16 * p, r0 = c0 + 16, R = HD_LEAF - r0;
-        if (warp == 0) {
-            // (a) 16 x 16 diagonal block: lane l (and its mirror l + 16) holds row l in registers; column j is
-            //     broadcast with shuffles.  No branches in the update: entries above the diagonal hold garbage that is
-            //     never read.  1 / L_jj comes from rsqrt (<= 1 ulp) and is kept for the substitutions.
-            const int l = lane & 15;
-            double a[16];
+    // (a) 16 x 16 diagonal block c0: lane l (and its mirror l + 16) holds row l in registers; column j is broadcast with
+    //     shuffles.  No branches in the update: entries above the diagonal hold garbage that is never read.  1 / L_jj comes from
+    //     rsqrt (<= 1 ulp) and is kept for the substitutions.  Executed by warp 0 only.
+    auto factor_diag = [&](const int c0) {
+        // Lane l (and its mirror l + 16) holds row l of the block in registers; fully unrolled over the 16 pivots.  Column j is
+        // broadcast through shared memory (double-buffered): 15 warp-wide double shuffles per pivot cost ~120 issue cycles on the
+        // single warp that runs this chain, 8 broadcast LDS.128 cost ~16.  Entries above the diagonal hold garbage that is
+        // never read.  Measured alternatives (tools/leafclk.py, cycles per 16 x 16 block, hot / first execution of a launch):
+        // this version 4.4k / 19k (the unrolled code is fetched cold by every launch); rolled loop with a shifting register row
+        // 7.9k / 8.6k; rolled loop in place on shared memory 14k / 15k.
+        const int l = lane & 15;
+        double a[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) a[k] = As[(c0 + k) * L2_LD + c0 + l];
+        for (int k = 0; k < 16; ++k) a[k] = As[(c0 + k) * L2_LD + c0 + l];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                double d = __shfl_sync(0xffffffffu, a[j], j);
-                double sj = 1.0;
-                if (LDL) {
-                    if (d < 0.0) { sj = -1.0; d = -d; }
-                    const double fl = *floorp;
-                    if (!(d > fl) || isinf(d)) { // tiny, zero or NaN pivot: static pivoting
-                        if (lane == 0) atomicAdd(nperturb, 1);
-                        d = fl; sj = 1.0;
-                    }
-                } else if (!(d > 0.0) || isinf(d)) {
-                    if (lane == 0) atomicCAS(info, 0, base + c0 + j + 1);
-                    d = 1.0;
+        for (int j = 0; j < 16; ++j) {
+            double d = __shfl_sync(0xffffffffu, a[j], j);
+            double sj = 1.0;
+            if (LDL) {
+                if (d < 0.0) { sj = -1.0; d = -d; }
+                const double fl = *floorp;
+                if (!(d > fl) || isinf(d)) { // tiny, zero or NaN pivot: static pivoting
+                    if (lane == 0) atomicAdd(nperturb, 1);
+                    d = fl; sj = 1.0;
                 }
-                const double ri = rsqrt(d);
-                const double r = d * ri;
-                a[j] = (l == j) ? r : a[j] * (LDL ? ri * sj : ri);
-                if (lane == 0) { Ri[c0 + j] = ri; if (LDL) Sg[c0 + j] = sj; }
-                const double aj = LDL ? sj * a[j] : a[j];
-#pragma unroll
-                for (int k = j + 1; k < 16; ++k) {
-                    const double t = __shfl_sync(0xffffffffu, a[j], k);
-                    a[k] = fma(-aj, t, a[k]);
-                }
+            } else if (!(d > 0.0) || isinf(d)) {
+                if (lane == 0) atomicCAS(info, 0, base + c0 + j + 1);
+                d = 1.0;
             }
-            if (lane < 16) {
+            const double ri = rsqrt(d);
+            const double r = d * ri;
+            a[j] = (l == j) ? r : a[j] * (LDL ? ri * sj : ri);
+            if (lane == 0) { Ri[c0 + j] = ri; if (LDL) Sg[c0 + j] = sj; }
+            const double aj = LDL ? sj * a[j] : a[j];
+            double *cb = Sc + (j & 1) * 16;
+            if (lane < 16) cb[l] = a[j];
+            __syncwarp();
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k <= l) As[(c0 + k) * L2_LD + c0 + l] = a[k];
+            for (int k = j + 1; k < 16; ++k) a[k] = fma(-aj, cb[k], a[k]);
+        }
+        __syncwarp();
+        if (lane < 16) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (k <= l) As[(c0 + k) * L2_LD + c0 + l] = a[k];
+        }
+    };
+    // (c) one 8-row tile row mt of the trailing update A22 -= X X^T (lower 8 x 8 tiles, four column tiles at a time so that
+    //     four independent DMMA chains are in flight); X = columns c0 .. c0+15, trailing block starts at r0
+    auto update_tile_row = [&](const int c0, const int r0, const int mt) {
+        const int m0 = r0 + 8 * mt;
+        double av[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) av[kk] = As[(c0 + 4 * kk + tig) * L2_LD + m0 + gid] * (LDL ? Sg[c0 + 4 * kk + tig] : 1.0);
+        for (int nt0 = 0; nt0 <= mt; nt0 += 4) {
+            double acc[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                double bv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bv[q] = As[(c0 + 4 * kk + tig) * L2_LD + r0 + 8 * min(nt0 + q, mt) + gid];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dmma_tile(acc[q][0], acc[q][1], av[kk], bv[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (nt0 + q > mt) continue;
+                const int n0 = r0 + 8 * (nt0 + q);
+                As[(n0 + 2 * tig) * L2_LD + m0 + gid] -= acc[q][0];
+                As[(n0 + 2 * tig + 1) * L2_LD + m0 + gid] -= acc[q][1];
             }
         }
-        __syncthreads();
-        LEAF_CLK(2 + 3 * p);
-        if (R == 0) break;
+    };
+    if (warp == 0) factor_diag(0);
+    __syncthreads();
+    LEAF_CLK(2);
+    for (int p = 0; p < 7; ++p) {
+        const int c0 = 16 * p, r0 = c0 + 16, R = HD_LEAF - r0;
         // (b) X = A21 L11^-T by (right-looking) forward substitution, one thread per row -- as dtrsm would: no explicit
         //     inverse on the factor itself, so a single-leaf matrix gets a classical, backward-stable Cholesky
         if (tid < R) {
@@ -210,36 +245,21 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base, doubl
         }
         __syncthreads();
         LEAF_CLK(3 + 3 * p);
-        // (c) A22 -= X X^T on the lower 8x8 tiles.  Warp w takes tile rows w and T-1-w (T+1 tiles together, balanced),
-        //     four column tiles at a time so that four independent DMMA chains are in flight
+        // (c) + look-ahead: warp 0 updates the next diagonal block (tile rows 0 and 1) and factors it at once -- the 16
+        //     sequential pivots of (a) are the longest dependency chain of a panel -- while warps 1..7 update the other tile
+        //     rows, two per warp (rows 2 + i and T - 1 - i: T + 2 tiles together, balanced)
         {
             const int T = R / 8;
-            for (int half = 0; half < 2; ++half) {
-                const int mt = half == 0 ? warp : T - 1 - warp;
-                if (mt < 0 || mt >= T || (half == 1 && mt <= warp) || (half == 0 && 2 * warp > T - 1)) continue;
-                const int m0 = r0 + 8 * mt;
-                double av[4];
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) av[kk] = As[(c0 + 4 * kk + tig) * L2_LD + m0 + gid] * (LDL ? Sg[c0 + 4 * kk + tig] : 1.0);
-                for (int nt0 = 0; nt0 <= mt; nt0 += 4) {
-                    double acc[4][2];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        double bv[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) bv[q] = As[(c0 + 4 * kk + tig) * L2_LD + r0 + 8 * min(nt0 + q, mt) + gid];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) dmma_tile(acc[q][0], acc[q][1], av[kk], bv[q]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (nt0 + q > mt) continue;
-                        const int n0 = r0 + 8 * (nt0 + q);
-                        As[(n0 + 2 * tig) * L2_LD + m0 + gid] -= acc[q][0];
-                        As[(n0 + 2 * tig + 1) * L2_LD + m0 + gid] -= acc[q][1];
-                    }
+            if (warp == 0) {
+                update_tile_row(c0, r0, 0);
+                update_tile_row(c0, r0, 1);
+                __syncwarp();
+                factor_diag(r0);
+            } else {
+                const int lo = 2 + (warp - 1), hi = T - 1 - (warp - 1);
+                if (lo <= hi) {
+                    update_tile_row(c0, r0, lo);
+                    if (hi != lo) update_tile_row(c0, r0, hi);
                 }
             }
         }

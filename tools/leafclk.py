@@ -12,6 +12,8 @@ for it in range(3):
     lib.hdsdpcu_linsys_numeric_dev(h, A.data_ptr(), n, ctypes.byref(info)); lib.hdsdpcu_sync()
 out=np.zeros(40,dtype=np.int64); lib.hdsdpcu_debug_leafclk(out.ctypes.data)
 t=out[:31]-out[0]
-print("load",t[1]); 
-for p in range(8): print("panel",p,"a",t[2+3*p]-(t[1] if p==0 else t[4+3*(p-1)]), "b",(t[3+3*p]-t[2+3*p]) if p<7 else 0,"c",(t[4+3*p]-t[3+3*p]) if p<7 else 0)
-print("afterloop",t[26]-t[23],"Lwriteback",t[27]-t[26],"W",t[28]-t[27],"phase2",t[29]-t[28],"dinv store",t[30]-t[29],"total",t[30])
+print("load",t[1], "first diag block (a)", t[2]-t[1])
+prev=t[2]
+for p in range(7):
+    print("panel",p,"(b) substitution",t[3+3*p]-prev,"(c)+next (a)",t[4+3*p]-t[3+3*p]); prev=t[4+3*p]
+print("Lwriteback",t[27]-t[26],"W",t[28]-t[27],"inverse",t[29]-t[28],"dinv store",t[30]-t[29],"total",t[30])
