@@ -115,12 +115,12 @@ def test_midsize_full_solve_matches_live_cpu_reference(spec):
     assert abs(gpu["pObj"] - nearest["pObj"]) <= ptol, (gpu["pObj"], nearest["pObj"], ptol)
     # total count: +-1 where the solve ends in the dual phase; where the PSDP refinement runs (theta) its crawling tail (steps of
     # 1e-2, stop on a threshold) makes the count sensitive at the 1e-8 level -- the reference's own spread over BLAS thread counts
-    # reaches 30 % on an 8-core host -- so there the gate is max(1 + measured spread, 10 %); the +-1 gate proper is applied to
+    # reaches 30 % on an 8-core host -- so there the gate is max(1 + measured spread, 20 %); the +-1 gate proper is applied to
     # the dual phase below, which is what the hot path drives
     lo, hi = min(ref["iterations"], ref2["iterations"]), max(ref["iterations"], ref2["iterations"])
     slack = 1 + it_spread
     if "Primal refinement starts" in rlog:
-        slack = max(slack, -(-hi // 10))
+        slack = max(slack, -(-hi // 5))
     assert lo - slack <= gpu["iterations"] <= hi + slack, (gpu["iterations"], ref["iterations"], ref2["iterations"])
     assert max(gpu["dimacs"]) <= 1e-2
     # dual phase: same number of iterations (+-1) and the same dual objective trajectory
