@@ -549,12 +549,22 @@ bool g_ss_attr = false;
 // =================================================================================================
 // creation
 // =================================================================================================
+static int cone_build(ConeCU *c, int nRow, int nCol, const int *beg, const int *idx, const double *elem);
+
 int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx, const double *elem) {
     if (hd_pad(nCol) > 46340) { // linear positions row + col * np are 32-bit (as the reference's own int indices)
         fprintf(stderr, "[hdsdpcu] cone_create: cone dimension %d is above the 32-bit index range of the dense dual matrix (46340)\n", nCol);
         return HD_FAILED;
     }
+    // the image is built by cone_build; a failure half-way (out of device memory, ...) releases whatever exists already
     ConeCU *c = new ConeCU();
+    const int rc = cone_build(c, nRow, nCol, beg, idx, elem);
+    if (rc != HD_OK) { cone_destroy(c); return rc; }
+    *pc = c;
+    return HD_OK;
+}
+
+static int cone_build(ConeCU *c, int nRow, int nCol, const int *beg, const int *idx, const double *elem) {
     c->m = nRow; c->n = nCol; c->np = hd_pad(nCol);
     const int m = nRow, n = nCol, np = c->np;
     c->coeff.resize(m + 1);
@@ -770,7 +780,7 @@ int cone_create(ConeCU **pc, int nRow, int nCol, const int *beg, const int *idx,
             HD_CALL(upload(&c->d_obj_full, full));
         }
     }
-    *pc = c;
+    (void) n;
     return HD_OK;
 }
 

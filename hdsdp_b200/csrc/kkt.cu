@@ -300,15 +300,11 @@ int hd_scale_vec(cudaStream_t st, double *x, int m, double a) {
     return HD_OK;
 }
 
-int kkt_create(KktCU **pk, int nRow) {
-    KktCU *k = new KktCU();
-    k->m = nRow;
-    k->mp = hd_pad(nRow);
+static int kkt_alloc(KktCU *k) {
     size_t bytes = sizeof(double) * (size_t) k->mp * k->mp;
-    if (cudaMalloc(&k->d_M, bytes) != cudaSuccess) { cudaGetLastError(); delete k; return HD_MEMORY; }
+    if (cudaMalloc(&k->d_M, bytes) != cudaSuccess) { cudaGetLastError(); k->d_M = nullptr; return HD_MEMORY; }
     HD_CUDA(cudaMemset(k->d_M, 0, bytes));
-    int rc = chol_create(&k->chol, nRow);
-    if (rc != HD_OK) { cudaFree(k->d_M); delete k; return rc; }
+    HD_CALL(chol_create(&k->chol, k->m));
     HD_CUDA(cudaMalloc(&k->d_asinv, sizeof(double) * k->mp));
     HD_CUDA(cudaMalloc(&k->d_asinvrd, sizeof(double) * k->mp));
     HD_CUDA(cudaMalloc(&k->d_asinvc, sizeof(double) * k->mp));
@@ -321,6 +317,15 @@ int kkt_create(KktCU **pk, int nRow) {
     HD_CUDA(cudaMalloc(&k->d_rhs, sizeof(double) * (size_t) k->mp * 8));
     HD_CUDA(cudaMemset(k->d_rhs, 0, sizeof(double) * (size_t) k->mp * 8));
     HD_CUDA(cudaMallocHost(&k->h_vec, sizeof(double) * (size_t) k->mp * 8));
+    return HD_OK;
+}
+
+int kkt_create(KktCU **pk, int nRow) {
+    KktCU *k = new KktCU();
+    k->m = nRow;
+    k->mp = hd_pad(nRow);
+    const int rc = kkt_alloc(k);
+    if (rc != HD_OK) { kkt_destroy(k); return rc; } // a failure half-way (20 GB for M at m = 50k) releases what exists already
     *pk = k;
     return HD_OK;
 }
@@ -329,7 +334,8 @@ void kkt_destroy(KktCU *k) {
     if (!k) return;
     cudaFree(k->d_M); cudaFree(k->d_asinv); cudaFree(k->d_asinvrd); cudaFree(k->d_asinvc);
     cudaFree(k->d_scal); cudaFree(k->d_rhs);
-    cudaFreeHost(k->h_scal); cudaFreeHost(k->h_vec);
+    if (k->h_scal) cudaFreeHost(k->h_scal);
+    if (k->h_vec) cudaFreeHost(k->h_vec);
     if (k->dist) dist_destroy(k->dist);
     if (k->d_gather) cudaFree(k->d_gather);
     if (k->d_ref) cudaFree(k->d_ref);

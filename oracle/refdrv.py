@@ -206,6 +206,12 @@ class RefKKT:
             raise RuntimeError(f"reference iteration failed rc={rc}")
         return {"build": t[0], "factorize": t[1], "solve": t[2], "total": t[3]}
 
+    def register_primal(self, Xs):
+        """HKKTRegisterPSDP: one n x n primal matrix per cone (used by HKKTBuildUp(KKT_TYPE_PRIMAL) in place of S^-1)."""
+        self._primal_keep = [np.asfortranarray(X, dtype=np.float64) for X in Xs]
+        self._primal_arr = (c_double_p * len(Xs))(*[_dp(X) for X in self._primal_keep])
+        self.l.refdrv_register_primal(self.h, self._primal_arr)
+
     def cg_status(self):
         """The reference's PCG-on-M state after the last solve: did it fall back to a Cholesky preconditioner?"""
         if not hasattr(self.l, "refdrv_cg_status"):

@@ -344,3 +344,33 @@ def test_reference_pcg_policy_on_device():
     assert np.linalg.norm(M2 @ x2 - b) <= 1e-6 * np.linalg.norm(b) * np.linalg.cond(M2) * 1e-10 + 1e-6
     kkt.set_solver(0)
     kkt.close(); cone.close()
+
+
+def test_primal_type_schur_matrix_against_live_reference():
+    """KKT_TYPE_PRIMAL (PSDP refinement, hdsdp_conic_sdp.c:1745-1756: the registered primal X takes the place of S^-1) at a
+    multi-leaf size against the REFERENCE's own HKKTBuildUp(KKT_TYPE_PRIMAL), not a numpy restatement."""
+    from hdsdp_b200 import api, problem
+    refdrv = need_ref()
+    n, ne = 300, 2500
+    prob = problem.gen_theta(n, ne, seed=2)
+    m = prob.m
+    rs = np.random.RandomState(21)
+    G = rs.standard_normal((n, n))
+    X = G @ G.T / n + np.eye(n)
+    X = 0.5 * (X + X.T)
+    ref = refdrv.RefKKT(prob)
+    y = np.zeros(m); y[0] = -(n + 10.0)
+    ref.set_point(y, 1.0, -1.0)
+    ref.register_primal([X])
+    ref.build(api.KKT_TYPE_PRIMAL)
+    Mr = np.tril(ref.get_M())
+    sdp, lps, kkt = api.build_problem(prob)
+    sdp[0].set_start(-1.0)
+    sdp[0].update(1.0, y)
+    assert sdp[0].factorize()
+    kkt.register_psdp([X])
+    kkt.build_up(api.KKT_TYPE_PRIMAL)
+    entry_ok(np.tril(kkt.get_matrix()), Mr, 1e-10, "PRIMAL-type Schur matrix")
+    v, vr = kkt.export(), ref.get_vectors()
+    entry_ok(v["dASinvVec"], vr["dASinvVec"], 1e-10, "PRIMAL-type dASinvVec")
+    ref.close(); kkt.close(); sdp[0].close()
