@@ -142,8 +142,8 @@ int hdsdpcu_linsys_symbolic(void *chol, int *colBeg, int *colIdx) { (void) chol;
 
 static int linsys_load_host(LinsysCU *l, const double *elem) {
     DenseChol *c = l->c;
-    HD_CUDA(cudaMemcpy2DAsync(c->L, (size_t) c->np * 8, elem, (size_t) c->n * 8, (size_t) c->n * 8, c->n,
-                              cudaMemcpyHostToDevice, g_stream));
+    HD_CALL(chol_ensure_work(c));
+    HD_CALL(hd_h2d_matrix(g_stream, c->L, c->np, elem, c->n, c->work));
     HD_CALL(hd_pad_identity(g_stream, c->L, c->np, c->n, c->np));
     c->factored = false;
     return HD_OK;
@@ -210,8 +210,7 @@ void hdsdpcu_linsys_invert(void *chol, double *fullInv, double *aux) {
         return;
     }
     if (chol_invert(g_stream, c, l->d_inv) != HD_OK) return;
-    HD_CUDA_VOID(cudaMemcpy2DAsync(fullInv, (size_t) c->n * 8, l->d_inv, (size_t) c->np * 8, (size_t) c->n * 8, c->n,
-                                   cudaMemcpyDeviceToHost, g_stream));
+    if (hd_d2h_matrix(g_stream, fullInv, l->d_inv, c->np, c->n, c->work) != HD_OK) return;   // work (X = L^-T) is dead after the product
     HD_CUDA_VOID(cudaStreamSynchronize(g_stream));
 }
 
@@ -438,15 +437,17 @@ int hdsdpcu_cone_setsinv_linsys(void *cone, void *chol) {
 
 int hdsdpcu_cone_getbuffer(void *cone, int which, double *out) {
     ConeCU *c = (ConeCU *) cone;
-    HD_CUDA(cudaMemcpy2DAsync(out, (size_t) c->n * 8, c->d_buf[which], (size_t) c->np * 8, (size_t) c->n * 8, c->n,
-                              cudaMemcpyDeviceToHost, g_stream));
+    double *stage = cone_scratch(c);
+    if (!stage) return HD_MEMORY;
+    HD_CALL(hd_d2h_matrix(g_stream, out, c->d_buf[which], c->np, c->n, stage));
     HD_CUDA(cudaStreamSynchronize(g_stream));
     return HD_OK;
 }
 int hdsdpcu_cone_getsinv(void *cone, double *out) {
     ConeCU *c = (ConeCU *) cone;
-    HD_CUDA(cudaMemcpy2DAsync(out, (size_t) c->n * 8, c->d_sinv, (size_t) c->np * 8, (size_t) c->n * 8, c->n,
-                              cudaMemcpyDeviceToHost, g_stream));
+    double *stage = cone_scratch(c);
+    if (!stage) return HD_MEMORY;
+    HD_CALL(hd_d2h_matrix(g_stream, out, c->d_sinv, c->np, c->n, stage));
     HD_CUDA(cudaStreamSynchronize(g_stream));
     return HD_OK;
 }

@@ -946,7 +946,7 @@ int cone_get_primal(ConeCU *c, double mu, const double *yHost, const double *dyH
     int t = (n + 31) / 32;
     HDK(primal_combine_kernel)<<<dim3(t, t), dim3(32, 8), 0, st>>>(c->d_prim, c->d_B, c->d_U, np, n, mu);
     HD_CUDA(cudaGetLastError());
-    HD_CUDA(cudaMemcpy2DAsync(Xhost, (size_t) n * 8, c->d_U, (size_t) np * 8, (size_t) n * 8, n, cudaMemcpyDeviceToHost, st));
+    HD_CALL(hd_d2h_matrix(st, Xhost, c->d_U, np, n, c->d_B));   // B is dead after the combine kernel
     HD_CUDA(cudaStreamSynchronize(st));
     return HD_OK;
 }
@@ -974,7 +974,7 @@ int cone_build_xsx(ConeCU *c, const double *Xhost, double *XSXhost, int iDualMat
     HD_CALL(hd_symmetrize_lower(st, c->d_buf[which], np, np));     // the strict upper triangle of the buffers is never read elsewhere
     double *X = c->d_prim;
     HD_CUDA(cudaMemsetAsync(X, 0, sizeof(double) * (size_t) np * np, st));
-    HD_CUDA(cudaMemcpy2DAsync(X, (size_t) np * 8, Xhost, (size_t) n * 8, (size_t) n * 8, n, cudaMemcpyHostToDevice, st));
+    HD_CALL(hd_h2d_matrix(st, X, np, Xhost, n, c->d_B));        // staged through B (written by the second product only)
     GemmArgs g{};
     g.M = np; g.N = np; g.K = np; g.alpha = 1.0; g.beta = 0.0; g.flags = 0;
     g.A = X; g.lda = np; g.B = c->d_buf[which]; g.ldb = np; g.C = c->d_U; g.ldc = np;    // U = X S
@@ -982,11 +982,11 @@ int cone_build_xsx(ConeCU *c, const double *Xhost, double *XSXhost, int iDualMat
     g.A = c->d_U; g.B = X; g.C = c->d_B;                                                  // R = U X
     HD_CALL(hd_gemm_nt(st, g));
     // accumulate into the caller's buffer on the device (one more n^2 each way keeps the += exact)
-    HD_CUDA(cudaMemcpy2DAsync(c->d_U, (size_t) np * 8, XSXhost, (size_t) n * 8, (size_t) n * 8, n, cudaMemcpyHostToDevice, st));
+    HD_CALL(hd_h2d_matrix(st, c->d_U, np, XSXhost, n, X));       // X is dead after the second product
     int t = (n + 31) / 32;
     HDK(xsx_accumulate_kernel)<<<dim3(t, t), dim3(32, 8), 0, st>>>(c->d_B, c->d_U, np, n);
     HD_CUDA(cudaGetLastError());
-    HD_CUDA(cudaMemcpy2DAsync(XSXhost, (size_t) n * 8, c->d_U, (size_t) np * 8, (size_t) n * 8, n, cudaMemcpyDeviceToHost, st));
+    HD_CALL(hd_d2h_matrix(st, XSXhost, c->d_U, np, n, X));
     HD_CUDA(cudaStreamSynchronize(st));
     return HD_OK;
 }
@@ -1012,11 +1012,13 @@ __global__ void lower_dot_kernel(const double *__restrict__ S, const double *__r
     if (threadIdx.x == 0) atomicAdd(out, 2.0 * red[0]);
 }
 
+double *cone_scratch(ConeCU *c) { return ensure_UB(c) == HD_OK ? c->d_U : nullptr; }
+
 int cone_xdots(ConeCU *c, const double *Xhost, double *out) {
     cudaStream_t st = hd_stream();
     const int n = c->n, np = c->np;
     HD_CALL(ensure_UB(c));
-    HD_CUDA(cudaMemcpy2DAsync(c->d_U, (size_t) np * 8, Xhost, (size_t) n * 8, (size_t) n * 8, n, cudaMemcpyHostToDevice, st));
+    HD_CALL(hd_h2d_matrix(st, c->d_U, np, Xhost, n, c->d_B));
     HD_CUDA(cudaMemsetAsync(c->d_scal + 6, 0, sizeof(double), st));
     long blocks = ((long) n * n + 255) / 256;
     if (blocks > 4 * hd_num_sms()) blocks = 4 * hd_num_sms();
@@ -1052,8 +1054,8 @@ int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT) {
     if (typeKKT == KKT_PRIMAL) {
         if (iCone >= (int) k->primalX.size() || !k->primalX[iCone]) return HD_FAILED; // hdsdp_conic_sdp.c:1747-1750
         HD_CUDA(cudaMemsetAsync(c->d_sinv, 0, sizeof(double) * (size_t) np * np, st));
-        HD_CUDA(cudaMemcpy2DAsync(c->d_sinv, (size_t) np * 8, k->primalX[iCone], (size_t) n * 8, (size_t) n * 8, n,
-                                  cudaMemcpyHostToDevice, st));
+        HD_CALL(ensure_UB(c));
+        HD_CALL(hd_h2d_matrix(st, c->d_sinv, np, k->primalX[iCone], n, c->d_U));
         c->sinv_valid = false;
     } else if (!c->sinv_valid) {
         if (!c->factor->factored) return HD_FAILED;

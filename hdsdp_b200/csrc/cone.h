@@ -155,6 +155,7 @@ int cone_factorize(ConeCU *c, int which, int *isPsd);
 int cone_build_schur(ConeCU *c, int iCone, KktCU *k, int typeKKT);
 int cone_build_xsx(ConeCU *c, const double *Xhost, double *XSXhost, int iDualMat);
 int cone_xdots(ConeCU *c, const double *Xhost, double *out);
+double *cone_scratch(ConeCU *c);   // np x np device scratch (allocated on first use)
 int cone_get_primal(ConeCU *c, double mu, const double *yHost, const double *dyHost, double *Xhost, int *isFeasible);
 // lanczos.cu
 int cone_ratio_test(ConeCU *c, double dTauStep, const double *dyHost, double dAdaRatio, int which, double *maxStep);

@@ -57,7 +57,32 @@ inline unsigned grid_for(long total, int threads) {
     return (unsigned) b;
 }
 
+__global__ void repack_kernel(double *__restrict__ dst, long ldd, const double *__restrict__ src, long lds, int n) {
+    const long total = (long) n * n;
+    for (long idx = (long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long) gridDim.x * blockDim.x) { // grid_for caps the grid
+        const int i = (int) (idx % n), j = (int) (idx / n);
+        dst[(long) j * ldd + i] = src[(long) j * lds + i];
+    }
+}
 } // namespace
+
+// Host <-> device transfer of an n x n column-major matrix whose device copy has leading dimension ld > n.  A 2-D copy between
+// PAGEABLE host memory and the device degenerates into one small transfer per column (~13 us each: 2.7 ms for n = 200); instead
+// the matrix travels contiguously through a device scratch buffer of n*n doubles and a kernel (un)packs it.
+int hd_h2d_matrix(cudaStream_t st, double *d_dst, long ldd, const double *h_src, int n, double *d_stage) {
+    if (ldd == n) { HD_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double) * (size_t) n * n, cudaMemcpyHostToDevice, st)); return HD_OK; }
+    HD_CUDA(cudaMemcpyAsync(d_stage, h_src, sizeof(double) * (size_t) n * n, cudaMemcpyHostToDevice, st));
+    HDK(repack_kernel)<<<grid_for((long) n * n, 256), 256, 0, st>>>(d_dst, ldd, d_stage, n, n);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+int hd_d2h_matrix(cudaStream_t st, double *h_dst, const double *d_src, long lds, int n, double *d_stage) {
+    if (lds == n) { HD_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * (size_t) n * n, cudaMemcpyDeviceToHost, st)); return HD_OK; }
+    HDK(repack_kernel)<<<grid_for((long) n * n, 256), 256, 0, st>>>(d_stage, n, d_src, lds, n);
+    HD_CUDA(cudaGetLastError());
+    HD_CUDA(cudaMemcpyAsync(h_dst, d_stage, sizeof(double) * (size_t) n * n, cudaMemcpyDeviceToHost, st));
+    return HD_OK;
+}
 
 int hd_set_identity(cudaStream_t st, double *A, long lda, int n) {
     HDK(set_identity_kernel)<<<grid_for((long) n * n, 256), 256, 0, st>>>(A, lda, n);
