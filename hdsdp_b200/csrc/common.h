@@ -150,4 +150,7 @@ int hd_symmetrize_lower(cudaStream_t st, double *A, long lda, int n);
 int hd_scale_vec(cudaStream_t st, double *x, int m, double a);
 int hd_h2d_matrix(cudaStream_t st, double *d_dst, long ldd, const double *h_src, int n, double *d_stage);
 int hd_d2h_matrix(cudaStream_t st, double *h_dst, const double *d_src, long lds, int n, double *d_stage);
+long hd_symv_ws_doubles(int np);
+int hd_symv_lower(cudaStream_t st, const double *A, long ld, int np, const double *d_x, long ldx, double *d_y, long ldy, int nRhs, double alpha,
+                  double *ws);
 int hd_copy2d(cudaStream_t st, double *dst, long ldd, const double *src, long lds, int rows, int cols);

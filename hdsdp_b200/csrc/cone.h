@@ -131,6 +131,7 @@ struct KktCU {
     int solver_mode = 0;
     bool use_jacobi = true;
     double *d_pcg = nullptr;        // [8 x mp + 8] CG vectors and scalars
+    double *d_symv_ws = nullptr;    // partial vectors of the ordered symv reduction (hd_symv_ws_doubles(mp))
     int last_cg_iters = 0, cg_solves = 0, cg_fallbacks = 0;
 };
 

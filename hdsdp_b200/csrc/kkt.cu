@@ -133,7 +133,7 @@ __global__ void lp_schur_kernel(const int *__restrict__ colptr, const int *__res
 constexpr int SV_N = 64;
 template <int NRHS>
 __global__ void __launch_bounds__(256, 2) symv_lower_kernel(const double *__restrict__ M, long ld, int nblk, const double *__restrict__ x,
-                                                           long ldx, double *y, long ldy) {
+                                                           long ldx, double *y, long ldy, double alpha, double *part) {
     __shared__ double xi[NRHS][HD_LEAF], xj[NRHS][SV_N];
     __shared__ double rowred[NRHS][2][HD_LEAF];
     __shared__ double colred[NRHS][4][SV_N];
@@ -185,15 +185,53 @@ __global__ void __launch_bounds__(256, 2) symv_lower_kernel(const double *__rest
         }
     }
     __syncthreads();
+    if (part) {
+        // deterministic mode: the tile's two partial vectors go to part[b][r][0..127 | 128..191]; symv_reduce_kernel adds them in order
+        double *pb = part + (b * NRHS) * (HD_LEAF + SV_N);
+        if (t < HD_LEAF) {
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) pb[r * (HD_LEAF + SV_N) + t] = rowred[r][0][t] + rowred[r][1][t];
+        } else if (t < HD_LEAF + SV_N) {
+            const int c = t - HD_LEAF;
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r) pb[r * (HD_LEAF + SV_N) + HD_LEAF + c] = colred[r][0][c] + colred[r][1][c] + colred[r][2][c] + colred[r][3][c];
+        }
+        return;
+    }
     if (t < HD_LEAF) {
 #pragma unroll
-        for (int r = 0; r < NRHS; ++r) atomicAdd(&y[(long) r * ldy + (long) i * HD_LEAF + t], rowred[r][0][t] + rowred[r][1][t]);
+        for (int r = 0; r < NRHS; ++r) atomicAdd(&y[(long) r * ldy + (long) i * HD_LEAF + t], alpha * (rowred[r][0][t] + rowred[r][1][t]));
     } else if (t < HD_LEAF + SV_N) {
         const int c = t - HD_LEAF;
 #pragma unroll
         for (int r = 0; r < NRHS; ++r)
-            atomicAdd(&y[(long) r * ldy + (long) j2 * SV_N + c], colred[r][0][c] + colred[r][1][c] + colred[r][2][c] + colred[r][3][c]);
+            atomicAdd(&y[(long) r * ldy + (long) j2 * SV_N + c], alpha * (colred[r][0][c] + colred[r][1][c] + colred[r][2][c] + colred[r][3][c]));
     }
+}
+
+// y[i-block] += alpha * (sum over the half-tiles of block row i of their row parts + sum over the half-tiles of block column i of
+// their column parts), in a fixed order: the result does not depend on the scheduling of symv_lower_kernel's CTAs
+template <int NRHS>
+__global__ void __launch_bounds__(HD_LEAF) symv_reduce_kernel(const double *__restrict__ part, int nblk, double *y, long ldy, double alpha) {
+    const int i = blockIdx.x, t = threadIdx.x;
+    constexpr int PW = HD_LEAF + SV_N;
+    double s[NRHS];
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
+    const long rowbase = (long) i * (i + 1);                   // first half-tile of block row i
+    for (int j2 = 0; j2 < 2 * (i + 1); ++j2) {
+        const double *pb = part + ((rowbase + j2) * NRHS) * PW;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) s[r] += pb[r * PW + t];
+    }
+    const int j2c = 2 * i + (t >> 6), c = t & 63;              // my 64-column block inside leaf i
+    for (int ii = i; ii < nblk; ++ii) {
+        const double *pb = part + (((long) ii * (ii + 1) + j2c) * NRHS) * PW;
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) s[r] += pb[r * PW + HD_LEAF + c];
+    }
+#pragma unroll
+    for (int r = 0; r < NRHS; ++r) y[(long) r * ldy + (long) i * HD_LEAF + t] += alpha * s[r];
 }
 
 // r <- b - r (r holds M x), and max |r_i| / max |b_i| per vector into out[2 v], out[2 v + 1]
@@ -340,6 +378,7 @@ void kkt_destroy(KktCU *k) {
     if (k->d_gather) cudaFree(k->d_gather);
     if (k->d_ref) cudaFree(k->d_ref);
     if (k->d_pcg) cudaFree(k->d_pcg);
+    if (k->d_symv_ws) cudaFree(k->d_symv_ws);
     chol_destroy(k->chol);
     delete k;
 }
@@ -497,20 +536,37 @@ int kkt_factorize(KktCU *k, int *info_out) {
     return info == 0 ? HD_OK : HD_FAILED;
 }
 
-// y (nrhs vectors of stride mp) += M x, M = the assembled Schur matrix (lower triangle), single GPU only
-int kkt_symv_dev(KktCU *k, const double *d_x, double *d_y, int nRhs) {
-    if (k->dist && k->nranks > 1) return HD_FAILED; // every rank holds only its own block columns of M
-    cudaStream_t st = hd_stream();
-    const int nb = k->mp / HD_LEAF;
+// y (nrhs vectors of stride ldy) += alpha * A x for a symmetric np x np matrix of which the lower triangle is stored (np % 128 == 0,
+// vectors zero-padded to np): used for the Schur matrix (PCG, residuals) and for the dual step dS of the Lanczos operator
+// ws: device workspace of hd_symv_ws_doubles(np) doubles for the deterministic (ordered) reduction; null = atomics
+long hd_symv_ws_doubles(int np) {
+    const long nb = np / HD_LEAF;
+    return nb * (nb + 1) * 2 * (HD_LEAF + SV_N);
+}
+int hd_symv_lower(cudaStream_t st, const double *A, long ld, int np, const double *d_x, long ldx, double *d_y, long ldy, int nRhs, double alpha,
+                  double *ws) {
+    const int nb = np / HD_LEAF;
     const long tiles = (long) nb * (nb + 1);   // 128 x 64 half-tiles of the lower triangle
     for (int r0 = 0; r0 < nRhs; r0 += 2) {
         const int nr = (nRhs - r0 >= 2) ? 2 : 1;
-        ++g_hd_launches;
-        if (nr == 2) symv_lower_kernel<2><<<(unsigned) tiles, 256, 0, st>>>(k->d_M, k->mp, nb, d_x + (long) r0 * k->mp, k->mp, d_y + (long) r0 * k->mp, k->mp);
-        else symv_lower_kernel<1><<<(unsigned) tiles, 256, 0, st>>>(k->d_M, k->mp, nb, d_x + (long) r0 * k->mp, k->mp, d_y + (long) r0 * k->mp, k->mp);
+        g_hd_launches += ws ? 2 : 1;
+        if (nr == 2) {
+            symv_lower_kernel<2><<<(unsigned) tiles, 256, 0, st>>>(A, ld, nb, d_x + (long) r0 * ldx, ldx, d_y + (long) r0 * ldy, ldy, alpha, ws);
+            if (ws) symv_reduce_kernel<2><<<nb, HD_LEAF, 0, st>>>(ws, nb, d_y + (long) r0 * ldy, ldy, alpha);
+        } else {
+            symv_lower_kernel<1><<<(unsigned) tiles, 256, 0, st>>>(A, ld, nb, d_x + (long) r0 * ldx, ldx, d_y + (long) r0 * ldy, ldy, alpha, ws);
+            if (ws) symv_reduce_kernel<1><<<nb, HD_LEAF, 0, st>>>(ws, nb, d_y + (long) r0 * ldy, ldy, alpha);
+        }
     }
     HD_CUDA(cudaGetLastError());
     return HD_OK;
+}
+
+// y (nrhs vectors of stride mp) += M x, M = the assembled Schur matrix (lower triangle), single GPU only
+int kkt_symv_dev(KktCU *k, const double *d_x, double *d_y, int nRhs) {
+    if (k->dist && k->nranks > 1) return HD_FAILED; // every rank holds only its own block columns of M
+    if (!k->d_symv_ws) HD_CUDA(cudaMalloc(&k->d_symv_ws, sizeof(double) * (size_t) hd_symv_ws_doubles(k->mp)));
+    return hd_symv_lower(hd_stream(), k->d_M, k->mp, k->mp, d_x, k->mp, d_y, k->mp, nRhs, 1.0, k->d_symv_ws);
 }
 
 

@@ -195,6 +195,7 @@ struct LanczosCU {
     double *v = nullptr, *w = nullptr, *z1 = nullptr, *z2 = nullptr, *warm = nullptr, *tmp = nullptr, *pert = nullptr;
     double *yv = nullptr;     // small device vector (eigenvector of the projected problem)
     double *scal = nullptr;   // device scalars
+    double *symv_ws = nullptr; // partial vectors of the ordered symv reduction
     double *h_scal = nullptr; // pinned
     double *h_H = nullptr;    // pinned
     int nComputed = 0;
@@ -211,6 +212,7 @@ static int lz_create(LanczosCU **pl, int n, int np) {
         HD_CUDA(cudaMalloc(p, sizeof(double) * np));
         HD_CUDA(cudaMemset(*p, 0, sizeof(double) * np));
     }
+    HD_CUDA(cudaMalloc(&l->symv_ws, sizeof(double) * (size_t) hd_symv_ws_doubles(np)));
     HD_CUDA(cudaMalloc(&l->yv, sizeof(double) * (LZ_DIM + 1)));
     HD_CUDA(cudaMalloc(&l->scal, sizeof(double) * 8));
     HD_CUDA(cudaMallocHost(&l->h_scal, sizeof(double) * 8));
@@ -222,7 +224,7 @@ static int lz_create(LanczosCU **pl, int n, int np) {
 void lz_destroy(LanczosCU *l) {
     if (!l) return;
     cudaFree(l->V); cudaFree(l->H); cudaFree(l->v); cudaFree(l->w); cudaFree(l->z1); cudaFree(l->z2); cudaFree(l->warm);
-    cudaFree(l->tmp); cudaFree(l->pert); cudaFree(l->yv); cudaFree(l->scal);
+    cudaFree(l->tmp); cudaFree(l->pert); cudaFree(l->yv); cudaFree(l->scal); cudaFree(l->symv_ws);
     cudaFreeHost(l->h_scal); cudaFreeHost(l->h_H);
     delete l;
 }
@@ -231,8 +233,9 @@ void lz_destroy(LanczosCU *l) {
 static int lz_matvec(ConeCU *c, DenseChol *f, cudaStream_t st, const double *in, double *out, double *tmp) {
     HD_CUDA(cudaMemcpyAsync(tmp, in, sizeof(double) * c->np, cudaMemcpyDeviceToDevice, st));
     HD_CALL(chol_bsolve(st, f, tmp, 1, c->np));                                   // L^T x = w
-    HDK(neg_symv_kernel)<<<(c->n + 127) / 128, 1024, 0, st>>>(c->d_buf[BUF_DUALSTEP], c->np, c->n, tmp, out);  // y = -dS x
-    HD_CUDA(cudaGetLastError());
+    // y = -dS x from the lower triangle of dS (read once, two CTAs per SM): the full-matrix kernel below ran on n / 128 CTAs only
+    HD_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * c->np, st));
+    HD_CALL(hd_symv_lower(st, c->d_buf[BUF_DUALSTEP], c->np, c->np, tmp, c->np, out, c->np, 1, -1.0, c->lanczos ? c->lanczos->symv_ws : nullptr));
     return chol_fsolve(st, f, out, 1, c->np);                                     // L z = y
 }
 
