@@ -107,6 +107,8 @@ int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "dist_delay") == 0) { hd_dist_set_delay(value); return HD_OK; }
     if (name && strcmp(name, "chol_sched") == 0) { hd_chol_set_sched(value); return HD_OK; }
     if (name && strcmp(name, "chol_leaf") == 0) { hd_chol_set_leaf(value); return HD_OK; }
+    if (name && strcmp(name, "ldl_pivot") == 0) { hd_chol_set_ldl_pivot(value); return HD_OK; }
+    if (name && strcmp(name, "chol_partition") == 0) { hd_chol_set_partition(value); return HD_OK; }
     if (name && strcmp(name, "trsv_version") == 0) { hd_trsv_set_version(value); return HD_OK; }
     if (name && strcmp(name, "chol_graph") == 0) { hd_chol_set_graph(value); return HD_OK; }
     return HD_FAILED;

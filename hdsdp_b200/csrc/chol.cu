@@ -379,6 +379,160 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base, doubl
     LEAF_CLK(30);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// LDL^T leaf with BOUNDED Bunch-Kaufman pivoting (the reference's indefinite fallback is LAPACK dsytrf,
+// linalg/hdsdp_linsolver.c:1662-1825: symmetric pivoting with 1 x 1 and 2 x 2 pivots).  Pivots are searched inside the
+// 128 x 128 diagonal leaf only, so the block recursion, the panel GEMMs and the multi-GPU layout stay as they are:
+//   P^T A P = L D L^T  (Bunch-Kaufman partial pivoting, alpha = (1 + sqrt 17) / 8, D block diagonal),
+//   D = Q Lambda Q^T per block  =>  A = G J G^T,  G = P L Q |Lambda|^(1/2),  J = sign(Lambda).
+// G is not triangular, but nothing outside the leaf ever reads a diagonal leaf of the factor: panels are solved with
+// the explicit G^-1 (trsm_rec), the triangular solves multiply by G^-1 / G^-T (trsv.cu), the updates use J.  The
+// kernel writes Dinv = |Lambda|^(-1/2) Q^T L^-1 P^T, the signs and (for checks only) G into the full leaf.  |lambda| <= *floorp
+// is replaced by +floorp and counted (static pivoting stays as the backstop for a leaf that is singular as a whole: pivots
+// are never taken from another leaf, so this is weaker than dsytrf -- the residual gate of the KKT solve covers the rest).
+// One CTA, the full symmetric leaf in shared memory; a fallback path, written for clarity: ~0.2 ms per leaf.
+constexpr int BK_LD = HD_LEAF + 1, BK_THREADS = 256;
+constexpr int BK_SMEM = (HD_LEAF * BK_LD + 4 * HD_LEAF) * 8;
+
+__device__ __forceinline__ void bk_argmax(double v, int idx, double *rv, int *ri, double &outv, int &outi) {
+    // largest v (ties: smallest idx) over the CTA; v < 0 / NaN never wins.  Ends with the scratch free for reuse.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!(v >= 0.0)) { v = -1.0; idx = 1 << 30; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if (lane == 0) { rv[warp] = v; ri[warp] = idx; }
+    __syncthreads();
+    outv = rv[0]; outi = ri[0];
+#pragma unroll
+    for (int w = 1; w < BK_THREADS / 32; ++w)
+        if (rv[w] > outv || (rv[w] == outv && ri[w] < outi)) { outv = rv[w]; outi = ri[w]; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(BK_THREADS, 1)
+ldl_bk_leaf_kernel(double *A, long lda, double *Dinv, double *sgn, const double *floorp, int *nperturb) {
+    extern __shared__ __align__(16) double sm[];
+    double *As = sm;                       // 128 x 129, column-major, FULL symmetric trailing matrix; L below the diagonal of finished columns
+    double *cu = sm + HD_LEAF * BK_LD;     // pivot column(s) and multipliers of the current step
+    double *cv = cu + HD_LEAF, *lu = cv + HD_LEAF, *lv = lu + HD_LEAF;
+    __shared__ int perm[HD_LEAF], bt[HD_LEAF];           // bt: 1 = 1 x 1 pivot, 2 / 0 = first / second column of a 2 x 2 pivot
+    __shared__ double lam[HD_LEAF], rcs[HD_LEAF], rsn[HD_LEAF];
+    __shared__ double rv[BK_THREADS / 32];
+    __shared__ int ri[BK_THREADS / 32];
+    const int tid = threadIdx.x, row = tid & 127, half = tid >> 7;
+    const double alpha = 0.6403882032022076, fl = *floorp;
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += BK_THREADS) {
+        const int i = e & 127, j = e >> 7;
+        As[j * BK_LD + i] = (i >= j) ? A[(long) j * lda + i] : A[(long) i * lda + j];
+    }
+    if (tid < HD_LEAF) perm[tid] = tid;
+    __syncthreads();
+    // symmetric interchange of rows / columns p and q (whole rows: also the finished columns of L)
+    auto swap_rc = [&](const int p, const int q) {
+        if (tid < HD_LEAF) { const double t = As[tid * BK_LD + p]; As[tid * BK_LD + p] = As[tid * BK_LD + q]; As[tid * BK_LD + q] = t; }
+        __syncthreads();
+        if (tid < HD_LEAF) { const double t = As[p * BK_LD + tid]; As[p * BK_LD + tid] = As[q * BK_LD + tid]; As[q * BK_LD + tid] = t; }
+        if (tid == 0) { const int t = perm[p]; perm[p] = perm[q]; perm[q] = t; }
+        __syncthreads();
+    };
+    int k = 0;
+    while (k < HD_LEAF) {
+        double lmax, sigma; int r, dummy;
+        bk_argmax((tid < HD_LEAF && tid > k) ? fabs(As[k * BK_LD + tid]) : -1.0, tid, rv, ri, lmax, r);
+        const double akk = fabs(As[k * BK_LD + k]);
+        int kind = 1;
+        if (lmax > 0.0 && !(akk >= alpha * lmax)) { // uniform over the CTA: every thread sees the same shared values
+            bk_argmax((tid < HD_LEAF && tid >= k && tid != r) ? fabs(As[r * BK_LD + tid]) : -1.0, tid, rv, ri, sigma, dummy);
+            const double arr = fabs(As[r * BK_LD + r]);
+            if (akk * sigma >= alpha * lmax * lmax) { }
+            else if (arr >= alpha * sigma) swap_rc(k, r);
+            else { kind = 2; if (r != k + 1) swap_rc(k + 1, r); }
+        }
+        if (kind == 1) {
+            double d = As[k * BK_LD + k];
+            if (!(fabs(d) > fl) || isinf(d)) { d = fl; if (tid == 0) atomicAdd(nperturb, 1); }
+            if (tid < HD_LEAF) { const double c = tid > k ? As[k * BK_LD + tid] : 0.0; cu[tid] = c; lu[tid] = c / d; }
+            __syncthreads();
+            if (row > k)
+                for (int j = k + 1 + half; j < HD_LEAF; j += 2) // (row, j) and (j, row) get the identical product: exact symmetry
+                    As[j * BK_LD + row] -= (row >= j) ? lu[row] * cu[j] : lu[j] * cu[row];
+            if (tid < HD_LEAF && tid > k) As[k * BK_LD + tid] = lu[tid];
+            if (tid == 0) { bt[k] = 1; lam[k] = d; rcs[k] = 1.0; rsn[k] = 0.0; }
+            k += 1;
+        } else {
+            const double a = As[k * BK_LD + k], b = As[k * BK_LD + k + 1], c = As[(k + 1) * BK_LD + k + 1];
+            double cs = 1.0, sn = 0.0, l1 = a, l2 = c; // Jacobi rotation: Q^T [a b; b c] Q = diag(l1, l2), Q = [cs sn; -sn cs]
+            if (b != 0.0) {
+                const double tau = (c - a) / (2.0 * b);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                cs = rsqrt(1.0 + t * t); sn = t * cs; l1 = a - t * b; l2 = c + t * b;
+            }
+            if (!(fabs(l1) > fl) || isinf(l1)) { l1 = fl; if (tid == 0) atomicAdd(nperturb, 1); }
+            if (!(fabs(l2) > fl) || isinf(l2)) { l2 = fl; if (tid == 0) atomicAdd(nperturb, 1); }
+            if (tid < HD_LEAF) {
+                const double u = tid > k + 1 ? As[k * BK_LD + tid] : 0.0, v = tid > k + 1 ? As[(k + 1) * BK_LD + tid] : 0.0;
+                const double q1 = (cs * u - sn * v) / l1, q2 = (sn * u + cs * v) / l2; // [u v] Q Lambda^-1
+                cu[tid] = u; cv[tid] = v;
+                lu[tid] = q1 * cs + q2 * sn; lv[tid] = -q1 * sn + q2 * cs;             // ... Q^T = [u v] D^-1
+            }
+            __syncthreads();
+            if (row > k + 1)
+                for (int j = k + 2 + half; j < HD_LEAF; j += 2)
+                    As[j * BK_LD + row] -= (row >= j) ? lu[row] * cu[j] + lv[row] * cv[j] : lu[j] * cu[row] + lv[j] * cv[row];
+            if (tid < HD_LEAF && tid > k + 1) { As[k * BK_LD + tid] = lu[tid]; As[(k + 1) * BK_LD + tid] = lv[tid]; }
+            if (tid == 0) {
+                As[k * BK_LD + k + 1] = 0.0; // L is unit lower with an identity 2 x 2 diagonal block
+                bt[k] = 2; bt[k + 1] = 0; lam[k] = l1; lam[k + 1] = l2;
+                rcs[k] = rcs[k + 1] = cs; rsn[k] = rsn[k + 1] = sn;
+            }
+            k += 2;
+        }
+        __syncthreads();
+    }
+    // G = P L Q |Lambda|^(1/2) back to the leaf of the factor (all 128 x 128 entries: G is not triangular once a pivot moved).
+    // Nothing on the solver path reads it; it is there so that A = G J G^T can be checked from outside.
+    {
+        auto Lf = [&](const int ii, const int cc) { return ii > cc ? As[cc * BK_LD + ii] : (ii == cc ? 1.0 : 0.0); };
+        for (int e = tid; e < HD_LEAF * HD_LEAF; e += BK_THREADS) {
+            const int ii = e & 127, cc = e >> 7, b = bt[cc];
+            double g;
+            if (b == 1) g = Lf(ii, cc);
+            else if (b == 2) g = rcs[cc] * Lf(ii, cc) - rsn[cc] * Lf(ii, cc + 1);
+            else g = rsn[cc] * Lf(ii, cc - 1) + rcs[cc] * Lf(ii, cc);
+            A[(long) cc * lda + perm[ii]] = g * sqrt(fabs(lam[cc]));
+        }
+    }
+    __syncthreads();
+    // Y = L^-1 in place (unit lower triangular; the diagonal is implicit): columns from the right,
+    // Y[j+1:, j] = -Y[j+1:, j+1:] L[j+1:, j]
+    for (int j = HD_LEAF - 2; j >= 0; --j) {
+        if (tid < HD_LEAF) cu[tid] = tid > j ? As[j * BK_LD + tid] : 0.0;
+        __syncthreads();
+        if (tid < HD_LEAF && tid > j) {
+            double s = cu[tid];
+            for (int t = j + 1; t < tid; ++t) s = fma(As[t * BK_LD + tid], cu[t], s);
+            As[j * BK_LD + tid] = -s;
+        }
+        __syncthreads();
+    }
+    // Dinv = |Lambda|^(-1/2) Q^T Y P^T : column perm[i] of Dinv is column i of Z = |Lambda|^(-1/2) Q^T Y
+    auto Y = [&](const int rr, const int ii) { return ii < rr ? As[ii * BK_LD + rr] : (ii == rr ? 1.0 : 0.0); };
+    for (int e = tid; e < HD_LEAF * HD_LEAF; e += BK_THREADS) {
+        const int rr = e & 127, ii = e >> 7, b = bt[rr];
+        const double sc = rsqrt(fabs(lam[rr]));
+        double z;
+        if (b == 1) z = Y(rr, ii);
+        else if (b == 2) z = rcs[rr] * Y(rr, ii) - rsn[rr] * Y(rr + 1, ii);
+        else z = rsn[rr] * Y(rr - 1, ii) + rcs[rr] * Y(rr, ii);
+        Dinv[(long) perm[ii] * HD_LEAF + rr] = z * sc;
+    }
+    if (tid < HD_LEAF) sgn[tid] = lam[tid] < 0.0 ? -1.0 : 1.0;
+}
+
 // X leaf (upper triangular) = Dinv^T
 __global__ void leaf_transpose_kernel(const double *__restrict__ Dinv, double *X, long ldx) {
     __shared__ double t[32][33];
@@ -457,9 +611,11 @@ int trsm_rec(cudaStream_t st, double *B, long ldb, int rows, const double *L, lo
 }
 
 int g_leaf_version = 2;
+int g_ldl_pivot = 1; // 1: bounded Bunch-Kaufman inside the leaf (default); 0: unpivoted L J L^T with static pivoting only
 int potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *info, int base) {
     if (n == HD_LEAF) {
-        if (g_ldl) { ++g_hd_launches; potf2_leaf2_kernel<true><<<1, L2_THREADS, L2_SMEM, st>>>(A, lda, dinv, info, base, sgn_of(dinv), g_ldl->floorp, g_ldl->nperturb); }
+        if (g_ldl && g_ldl_pivot) { ++g_hd_launches; ldl_bk_leaf_kernel<<<1, BK_THREADS, BK_SMEM, st>>>(A, lda, dinv, sgn_of(dinv), g_ldl->floorp, g_ldl->nperturb); }
+        else if (g_ldl) { ++g_hd_launches; potf2_leaf2_kernel<true><<<1, L2_THREADS, L2_SMEM, st>>>(A, lda, dinv, info, base, sgn_of(dinv), g_ldl->floorp, g_ldl->nperturb); }
         else if (g_leaf_version == 2) { ++g_hd_launches; potf2_leaf2_kernel<false><<<1, L2_THREADS, L2_SMEM, st>>>(A, lda, dinv, info, base, nullptr, nullptr, nullptr); }
         else HDK(potf2_leaf_kernel)<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, dinv, info, base);
         HD_CUDA(cudaGetLastError());
@@ -507,6 +663,7 @@ static int ensure_leaf_attr() {
         HD_CUDA(cudaFuncSetAttribute(potf2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
         HD_CUDA(cudaFuncSetAttribute(potf2_leaf2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
         HD_CUDA(cudaFuncSetAttribute(potf2_leaf2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+        HD_CUDA(cudaFuncSetAttribute(ldl_bk_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
         attr |= 1ull << (dev & 63);
     }
     return HD_OK;
@@ -601,6 +758,7 @@ static int g_lookahead_nb = -1; // block size; 0 disables the blocked path; -1 =
 
 void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
 void hd_chol_set_leaf(int v) { g_leaf_version = v; }
+void hd_chol_set_ldl_pivot(int v) { g_ldl_pivot = v != 0; }
 int hd_leaf_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_leaf_clk, sizeof(long long) * 40) == cudaSuccess ? HD_OK : HD_FAILED; }
 
 static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
@@ -866,7 +1024,7 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     // -3 % at 4096, +2 % at 8192 and beyond (stream priorities are not honoured inside a graph), hence the size limit.
     const unsigned long long key = 1ull | ((unsigned long long) nb << 8) | ((unsigned long long) (c->ldl ? 1 : 0) << 1) |
                                    ((unsigned long long) g_leaf_version << 2) | ((unsigned long long) hd_gemm_get_variant() << 4) |
-                                   ((unsigned long long) (g_sched + 1) << 40);
+                                   ((unsigned long long) (g_sched + 1) << 40) | ((unsigned long long) g_ldl_pivot << 44);
     const bool graph_ok = g_use_graph && c->np <= g_graph_max && getenv("HDSDPCU_TRACE") == nullptr;
     if (graph_ok && c->graph_exec && c->graph_key == key) {
         HD_CUDA(cudaGraphLaunch((cudaGraphExec_t) c->graph_exec, st));

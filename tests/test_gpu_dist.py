@@ -65,6 +65,8 @@ def test_distributed_ldl_mode(n, nb, P, nneg):
     assert set(np.unique(sg)) <= {-1.0, 1.0} and int((sg < 0).sum()) == int((np.linalg.eigvalsh(A) < 0).sum())
     for L in (L0, L1):
         T = np.tril(L)
+        for s0 in range(0, n, 128):     # diagonal leaves are G = P L Q |Lambda|^(1/2) of the bounded Bunch-Kaufman leaf: all entries count
+            T[s0:s0 + 128, s0:s0 + 128] = L[s0:s0 + 128, s0:s0 + 128]
         assert np.isfinite(T).all()
         assert np.abs((T * sg) @ T.T - A).max() <= 1e-11 * np.abs(A).max() * n
 

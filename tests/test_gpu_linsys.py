@@ -167,6 +167,90 @@ def test_indefinite_backend_static_pivot():
     ls.close()
 
 
+def sym_needs_pivoting(n, kind, seed):
+    """Symmetric indefinite matrices on which an UNPIVOTED L D L^T meets zero / tiny pivots at once: a scaled GOE matrix with a
+    zero diagonal, and a saddle-point matrix [[H, B^T], [B, 0]] under a random symmetric permutation (half of the diagonal is 0)."""
+    rs = np.random.RandomState(seed)
+    if kind == "zero_diag":
+        B = rs.standard_normal((n, n))
+        A = (B + B.T) / np.sqrt(2.0 * n)
+        np.fill_diagonal(A, 0.0)
+        return A
+    h = n // 2
+    G = rs.standard_normal((h, h))
+    H = G @ G.T / h + np.eye(h)
+    Bm = rs.standard_normal((n - h, h)) / np.sqrt(h)
+    A = np.block([[H, Bm.T], [Bm, np.zeros((n - h, n - h))]])
+    p = rs.permutation(n)
+    return A[np.ix_(p, p)]
+
+
+@pytest.mark.parametrize("n,kind", [(100, "zero_diag"), (128, "saddle"), (300, "zero_diag"), (1000, "saddle"), (1024, "zero_diag"),
+                                    (2500, "zero_diag")])
+def test_indefinite_backend_bounded_bunch_kaufman(n, kind):
+    """Reference a15: the fallback is dsytrf, i.e. SYMMETRIC PIVOTING with 1 x 1 and 2 x 2 pivots (hdsdp_linsolver.c:1662-1825).
+    The device searches its pivots inside every 128 x 128 leaf (bounded Bunch-Kaufman, chol.cu ldl_bk_leaf_kernel): matrices
+    whose diagonal is (half) zero factor without a single perturbed pivot, with the inertia of the matrix and a backward error
+    of the order of LAPACK's -- and without the pivoting (option ldl_pivot = 0, the round-1 behaviour) they do not."""
+    import ctypes
+    from hdsdp_b200 import _lib
+    from hdsdp_b200.api import DenseLinsys
+    A = np.asfortranarray(sym_needs_pivoting(n, kind, 3 * n + 1))
+    lib = _lib.require_gpu()
+    rs = np.random.RandomState(4)
+    B = rs.standard_normal((n, 2))
+    normA = np.abs(A).sum(axis=1).max()
+
+    def run():
+        ls = DenseLinsys(n)
+        assert lib.hdsdpcu_linsys_set_indefinite(ls.h, 1) == 0
+        assert ls.numeric(A) == 0
+        neg, pert = ctypes.c_int(-1), ctypes.c_int(-1)
+        assert lib.hdsdpcu_linsys_inertia(ls.h, ctypes.byref(neg), ctypes.byref(pert)) == 0
+        X = ls.solve(B)
+        ls.close()
+        berr = np.abs(A @ X - B).max() / (normA * np.abs(X).max() + np.abs(B).max()) if np.isfinite(X).all() else np.inf
+        return neg.value, pert.value, X, berr
+
+    neg, pert, X, berr = run()
+    assert pert == 0
+    assert neg == int((np.linalg.eigvalsh(A) < 0).sum())                                  # Sylvester: inertia of J
+    Xl = np.linalg.solve(A, B)                                                            # LAPACK dgesv
+    berr_lapack = np.abs(A @ Xl - B).max() / (normA * np.abs(Xl).max() + np.abs(B).max())
+    assert berr <= max(1e-12, 1e3 * berr_lapack), (berr, berr_lapack)
+    assert np.abs(X - Xl).max() <= 1e-9 * np.linalg.cond(A) * np.abs(Xl).max()
+    try:                                                                                  # contrast: static pivoting alone
+        assert lib.hdsdpcu_set_option(b"ldl_pivot", 0) == 0
+        _, pert0, _, berr0 = run()
+        assert pert0 > 0 or berr0 > 1e3 * berr
+    finally:
+        lib.hdsdpcu_set_option(b"ldl_pivot", 1)
+
+
+def test_bunch_kaufman_leaf_agrees_with_static_ldl_where_no_pivoting_is_needed():
+    """On a block-diagonally dominant indefinite matrix both variants are stable: same inertia, solutions equal to 1e-12."""
+    from hdsdp_b200 import _lib
+    from hdsdp_b200.api import DenseLinsys
+    lib = _lib.require_gpu()
+    n = 700
+    A, _ = sym_indefinite(n, 21, 50)
+    A = np.asfortranarray(A)
+    b = np.random.RandomState(2).standard_normal(n)
+    xs = []
+    try:
+        for piv in (1, 0):
+            assert lib.hdsdpcu_set_option(b"ldl_pivot", piv) == 0
+            ls = DenseLinsys(n)
+            lib.hdsdpcu_linsys_set_indefinite(ls.h, 1)
+            assert ls.numeric(A) == 0
+            xs.append(ls.solve(b))
+            ls.close()
+    finally:
+        lib.hdsdpcu_set_option(b"ldl_pivot", 1)
+    assert np.abs(xs[0] - xs[1]).max() <= 1e-12 * np.abs(xs[0]).max()
+    assert np.abs(A @ xs[0] - b).max() <= 1e-12 * np.abs(b).max() * n
+
+
 @pytest.mark.parametrize("leaf,trsv", [(1, 1), (1, 2), (2, 1)])
 def test_alternative_kernel_versions(leaf, trsv):
     """The measurement knobs (include/hdsdpcu.h hdsdpcu_set_option) select older kernel generations: they must stay correct."""
