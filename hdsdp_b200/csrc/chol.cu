@@ -13,6 +13,7 @@
 // The recursion runs on the host and only enqueues kernels on one stream; shapes are fixed per
 // matrix size, so a whole factorisation can be captured into a CUDA graph by the caller.
 #include "common.h"
+#include <cuda.h>
 #include <cmath>
 #include <vector>
 
@@ -858,6 +859,78 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
 //   UPDREST(k) everything from block column k+3 on (one lower-triangular GEMM, K = NB)
 // The side stream waits for the main stream only when the bulk falls more than one step behind.
 static std::vector<cudaEvent_t> g_evs[4]; // potrf, strip (side -> main); col, col2 (main -> side)
+
+// Optional SM partition for the strip schedule (CUDA green contexts; driver API resolved through the runtime so that the
+// library has no link-time dependency on libcuda): the chain gets 8 SMs of its own (the smallest partition sm_100 allows),
+// the bulk GEMMs the other 140.  The idea: a high-priority stream only wins the NEXT free CTA slot, so a chain kernel waits
+// behind bulk CTAs that run for 20 .. 40 us.  MEASURED ON B200 AND REJECTED (tools/trace_potrf.py, ms without / with the
+// partition): n = 4096 2.44 / 2.45, 6144 5.28 / 5.38, 8192 9.63 / 9.78, 10240 16.3 / 16.8 -- the 5 % of SMs the bulk loses
+// cost more than the slot waits.  Kept behind hdsdpcu_set_option("chol_partition", 1), off by default.
+struct SmPartition { bool tried = false; cudaStream_t chain = nullptr, bulk = nullptr; int chain_sms = 0, bulk_sms = 0; };
+static SmPartition g_part[64];
+static int g_partition = 0;
+static cudaEvent_t g_ev_join = nullptr;
+void hd_chol_set_partition(int v) { g_partition = v; }
+
+template <typename F> static bool drv_entry(const char *name, F &fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !ptr) {
+        cudaGetLastError();
+        return false;
+    }
+    fn = reinterpret_cast<F>(ptr);
+    return true;
+}
+
+static SmPartition *sm_partition() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SmPartition &P = g_part[dev & 63];
+    if (P.tried) return P.chain ? &P : nullptr;
+    P.tried = true;
+    decltype(&cuDeviceGet) pDeviceGet = nullptr;
+    decltype(&cuDeviceGetDevResource) pGetRes = nullptr;
+    decltype(&cuDevSmResourceSplitByCount) pSplit = nullptr;
+    decltype(&cuDevResourceGenerateDesc) pDesc = nullptr;
+    decltype(&cuGreenCtxCreate) pCreate = nullptr;
+    decltype(&cuGreenCtxStreamCreate) pStream = nullptr;
+    if (!drv_entry("cuDeviceGet", pDeviceGet) || !drv_entry("cuDeviceGetDevResource", pGetRes) ||
+        !drv_entry("cuDevSmResourceSplitByCount", pSplit) || !drv_entry("cuDevResourceGenerateDesc", pDesc) ||
+        !drv_entry("cuGreenCtxCreate", pCreate) || !drv_entry("cuGreenCtxStreamCreate", pStream)) {
+        fprintf(stderr, "[hdsdpcu] green contexts not available in this driver: SM partition off\n");
+        return nullptr;
+    }
+    CUdevice cudev;
+    CUdevResource all, grp[1], rest;
+    unsigned int ngrp = 1;
+    CUdevResourceDesc d_chain = nullptr, d_bulk = nullptr;
+    CUgreenCtx c_chain = nullptr, c_bulk = nullptr;
+    CUstream s_chain = nullptr, s_bulk = nullptr;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (pDeviceGet(&cudev, dev) != CUDA_SUCCESS || pGetRes(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
+        pSplit(grp, &ngrp, &all, &rest, 0, 8) != CUDA_SUCCESS || ngrp < 1 || rest.sm.smCount < 64 ||
+        pDesc(&d_chain, &grp[0], 1) != CUDA_SUCCESS || pDesc(&d_bulk, &rest, 1) != CUDA_SUCCESS ||
+        pCreate(&c_chain, d_chain, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+        pCreate(&c_bulk, d_bulk, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+        pStream(&s_chain, c_chain, CU_STREAM_NON_BLOCKING, hi) != CUDA_SUCCESS ||
+        pStream(&s_bulk, c_bulk, CU_STREAM_NON_BLOCKING, lo) != CUDA_SUCCESS) {
+        fprintf(stderr, "[hdsdpcu] SM partition could not be created: off\n");
+        cudaGetLastError();
+        return nullptr;
+    }
+    P.chain = (cudaStream_t) s_chain; P.bulk = (cudaStream_t) s_bulk;
+    P.chain_sms = (int) grp[0].sm.smCount; P.bulk_sms = (int) rest.sm.smCount;
+    if (getenv("HDSDPCU_TRACE")) fprintf(stderr, "[trace] SM partition: chain %d SMs, bulk %d SMs\n", P.chain_sms, P.bulk_sms);
+    return &P;
+}
+int hd_chol_partition_sms(int *chain, int *bulk) {
+    SmPartition *P = sm_partition();
+    if (chain) *chain = P ? P->chain_sms : 0;
+    if (bulk) *bulk = P ? P->bulk_sms : 0;
+    return P ? HD_OK : HD_FAILED;
+}
 static cudaEvent_t g_ev_fork = nullptr;
 
 static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
@@ -881,7 +954,16 @@ static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *
     auto leaves = [&](int k) { return dinv + (long) (start(k) / HD_LEAF) * HD_LEAF * HD_LEAF; };
     auto at = [&](int r, int c) { return A + (long) c * lda + r; };
     cudaStream_t side = g_side;
+    cudaStream_t const caller = st;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    SmPartition *part = (g_partition > 0 && cap == cudaStreamCaptureStatusNone) ? sm_partition() : nullptr;
     HD_CUDA(cudaEventRecord(g_ev_fork, st));
+    if (part) {
+        side = part->chain;
+        st = part->bulk; // from here on "st" is the bulk stream; the caller's stream only forks and joins
+        HD_CUDA(cudaStreamWaitEvent(st, g_ev_fork, 0));
+    }
     HD_CUDA(cudaStreamWaitEvent(side, g_ev_fork, 0));
     for (int k = 0; k < nblk; ++k) {
         const int s0 = start(k), b0 = size(k), s1 = start(k + 1), b1 = size(k + 1), s2 = start(k + 2), b2 = size(k + 2), s3 = start(k + 3);
@@ -946,6 +1028,11 @@ static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *
         }
     }
     HD_CUDA(cudaStreamWaitEvent(st, g_evs[0][nblk - 1], 0)); // join
+    if (part) {
+        if (!g_ev_join) HD_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+        HD_CUDA(cudaEventRecord(g_ev_join, st));
+        HD_CUDA(cudaStreamWaitEvent(caller, g_ev_join, 0));
+    }
     return HD_OK;
 }
 
@@ -1024,7 +1111,7 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     // -3 % at 4096, +2 % at 8192 and beyond (stream priorities are not honoured inside a graph), hence the size limit.
     const unsigned long long key = 1ull | ((unsigned long long) nb << 8) | ((unsigned long long) (c->ldl ? 1 : 0) << 1) |
                                    ((unsigned long long) g_leaf_version << 2) | ((unsigned long long) hd_gemm_get_variant() << 4) |
-                                   ((unsigned long long) (g_sched + 1) << 40) | ((unsigned long long) g_ldl_pivot << 44);
+                                   ((unsigned long long) (g_sched + 1) << 40) | ((unsigned long long) g_ldl_pivot << 44) | ((unsigned long long) (g_partition > 0) << 45);
     const bool graph_ok = g_use_graph && c->np <= g_graph_max && getenv("HDSDPCU_TRACE") == nullptr;
     if (graph_ok && c->graph_exec && c->graph_key == key) {
         HD_CUDA(cudaGraphLaunch((cudaGraphExec_t) c->graph_exec, st));

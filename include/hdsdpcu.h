@@ -55,8 +55,7 @@ int hdsdpcu_debug_leafclk(long long *out);
  *   "ldl_pivot"    LDL^T fallback: 1 (default) = bounded Bunch-Kaufman pivoting (1 x 1 and 2 x 2 pivots) inside every 128 x 128
  *                  leaf; 0 = unpivoted L J L^T with static pivoting only (round-1 behaviour)
  *   "chol_partition" strip schedule: 1 = the chain runs in an 8-SM green-context partition, the bulk GEMMs in the other 140 SMs;
- *                  0 = both share all SMs (stream priorities only); -1 (default) = on where the factorisation is not replayed
- *                  from a graph (n > 6144) and the strip schedule is used (n <= 10240)
+ *                  0 (default) = both share all SMs (stream priorities only).  Measured slower on B200
  *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default)
  *   "chol_graph"   1 (default): factorisations up to n = 6144 are replayed from a captured CUDA graph from their third call on */
 int hdsdpcu_set_option(const char *name, int value);

@@ -6,7 +6,7 @@ from hdsdp_b200 import _lib
 from hdsdp_b200.api import DenseLinsys
 from test_gpu_linsys import sym_needs_pivoting
 lib = _lib.require_gpu()
-for n, kind in [(100, "zero_diag"), (128, "saddle"), (300, "zero_diag"), (1000, "saddle"), (1024, "zero_diag"), (2500, "zero_diag"), (2048, "saddle")]:
+for n, kind in [(128, "saddle"), (1024, "saddle"), (2048, "saddle"), (1024, "zero_diag")]:
     A = np.asfortranarray(sym_needs_pivoting(n, kind, 3 * n + 1))
     B = np.random.RandomState(4).standard_normal((n, 2))
     normA = np.abs(A).sum(axis=1).max()
