@@ -85,8 +85,11 @@ void hdsdpcu_linsys_invert(void *chol, double *fullInv, double *aux);           
 void hdsdpcu_linsys_destroy(void **pchol);                                            /* cholDestroy */
 /* Indefinite back-end (reference lapackIndefiniteLinSolver*, dsytrf/dsytrs, linalg/hdsdp_linsolver.c:1662-1825, selected by
  * HFpLinsysSwitchToIndefinite :1827 when dpotrf of the Schur matrix fails): with set_indefinite(1) numeric computes the
- * unpivoted factorisation A = L J L^T, J = diag(+-1), with static pivoting (|pivot| <= 1e-13 max|A_ii| is replaced), solve
- * applies L^-1, J, L^-T.  Not Bunch-Kaufman: meant for the "almost indefinite" Schur matrices the reference switches on. */
+ * factorisation A = L J L^T, J = diag(+-1), whose 128 x 128 diagonal leaves are factored with Bunch-Kaufman pivoting
+ * (1 x 1 and 2 x 2 pivots, as dsytrf; the pivot search is bounded to the leaf, so the block recursion and the multi-GPU
+ * layout are those of the Cholesky path) and static pivoting as the backstop (an eigenvalue of a pivot block with
+ * |lambda| <= 1e-13 max|A_ii| is replaced and counted); solve applies L^-1, J, L^-T.  set_option("ldl_pivot", 0) gives the
+ * unpivoted round-1 variant. */
 int  hdsdpcu_linsys_set_indefinite(void *chol, int on);
 int  hdsdpcu_linsys_inertia(void *chol, int *nNegative, int *nPerturbed);
 /* device-resident variants (no host round trip): d_elem has leading dimension ld >= nCol */
