@@ -170,19 +170,32 @@ __global__ void __launch_bounds__(256, 2) symv_lower_kernel(const double *__rest
         for (int q = 0; q < 32; ++q) acc += tl[q] * xj[r][half * 32 + q];
         rowred[r][half][row] = acc;
     }
-    // transposed part: column c = half*32 + q gets sum_row T[row, c] x_i[row]; on a diagonal leaf the diagonal itself was
-    // already used by the row product
+    // transposed part: column c = half*32 + q gets sum_row T[row, c] x_i[row]
+    // Reduction of the 32 column products over the 32 lanes by recursive halving: at distance s a lane keeps the half of its
+    // values whose index has bit s equal to its own lane bit and hands the other half to its partner -- 16 + 8 + 4 + 2 + 1 = 31
+    // shuffles instead of 32 x 5, and lane q ends with the total of column q (the tile's compute phase was what kept the
+    // kernel at 63 % of HBM: 2 CTAs/SM cannot hide 160 shuffles per thread behind the other CTA's loads).
+    if (diag) { // on a diagonal leaf the diagonal itself was already used by the row product
+#pragma unroll
+        for (int q = 0; q < 32; ++q) if (c0 + half * 32 + q == row) tl[q] = 0.0;
+    }
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) {
         const double xv = xi[r][row];
+        double v[16];
+        const bool up16 = (lane & 16) != 0;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            double v = tl[q] * xv;
-            if (diag && c0 + half * 32 + q == row) v = 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == q) colred[r][w4][half * 32 + q] = v;
+        for (int q = 0; q < 16; ++q) {
+            const double lo = tl[q] * xv, hi = tl[q + 16] * xv;
+            v[q] = (up16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, up16 ? lo : hi, 16);
         }
+#pragma unroll
+        for (int sdist = 8; sdist >= 1; sdist >>= 1) {
+            const bool up = (lane & sdist) != 0;
+#pragma unroll
+            for (int q = 0; q < sdist; ++q) v[q] = (up ? v[q + sdist] : v[q]) + __shfl_xor_sync(0xffffffffu, up ? v[q] : v[q + sdist], sdist);
+        }
+        colred[r][w4][half * 32 + lane] = v[0];
     }
     __syncthreads();
     if (part) {
