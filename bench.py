@@ -266,6 +266,7 @@ class HotPath:
             self.kkt.build_up_extra_bound(lo * lo + up * up, up - lo)
 
     def step_device(self, s, timed, regularize=True):
+        s = s % len(self.y_host)  # fewer prepared points than steps (tiny --steps/--warmup): reuse them
         from ctypes import byref, c_int
         lib, check = self.lib, self._lib.check
         flag = c_int(0)
@@ -291,6 +292,7 @@ class HotPath:
             self.fact_ms.append(e0.elapsed_time(e1))
 
     def step_host(self, s, regularize=True):
+        s = s % len(self.y_host)  # fewer prepared points than steps (tiny --steps/--warmup): reuse them
         y = self.y_host[s]
         for c in self.sdp:
             c.update(self.tau, y)

@@ -224,27 +224,39 @@ __global__ void __launch_bounds__(256, 2) symv_lower_kernel(const double *__rest
 
 // y[i-block] += alpha * (sum over the half-tiles of block row i of their row parts + sum over the half-tiles of block column i of
 // their column parts), in a fixed order: the result does not depend on the scheduling of symv_lower_kernel's CTAs
+constexpr int SVR_G = 8; // groups of 128 threads per block row: group g adds the partial vectors of tiles g, g + 8, ...
 template <int NRHS>
-__global__ void __launch_bounds__(HD_LEAF) symv_reduce_kernel(const double *__restrict__ part, int nblk, double *y, long ldy, double alpha) {
-    const int i = blockIdx.x, t = threadIdx.x;
+__global__ void __launch_bounds__(HD_LEAF * SVR_G) symv_reduce_kernel(const double *__restrict__ part, int nblk, double *y, long ldy, double alpha) {
+    __shared__ double gs[SVR_G][NRHS][HD_LEAF];
+    const int i = blockIdx.x, t = threadIdx.x & (HD_LEAF - 1), g = threadIdx.x >> 7;
     constexpr int PW = HD_LEAF + SV_N;
     double s[NRHS];
 #pragma unroll
     for (int r = 0; r < NRHS; ++r) s[r] = 0.0;
     const long rowbase = (long) i * (i + 1);                   // first half-tile of block row i
-    for (int j2 = 0; j2 < 2 * (i + 1); ++j2) {
+    for (int j2 = g; j2 < 2 * (i + 1); j2 += SVR_G) {
         const double *pb = part + ((rowbase + j2) * NRHS) * PW;
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) s[r] += pb[r * PW + t];
     }
     const int j2c = 2 * i + (t >> 6), c = t & 63;              // my 64-column block inside leaf i
-    for (int ii = i; ii < nblk; ++ii) {
+    for (int ii = i + g; ii < nblk; ii += SVR_G) {
         const double *pb = part + (((long) ii * (ii + 1) + j2c) * NRHS) * PW;
 #pragma unroll
         for (int r = 0; r < NRHS; ++r) s[r] += pb[r * PW + HD_LEAF + c];
     }
 #pragma unroll
-    for (int r = 0; r < NRHS; ++r) y[(long) r * ldy + (long) i * HD_LEAF + t] += alpha * s[r];
+    for (int r = 0; r < NRHS; ++r) gs[g][r][t] = s[r];
+    __syncthreads();
+    if (g == 0) {
+#pragma unroll
+        for (int r = 0; r < NRHS; ++r) {
+            double v = gs[0][r][t];
+#pragma unroll
+            for (int q = 1; q < SVR_G; ++q) v += gs[q][r][t];  // fixed order: the sum does not depend on the schedule
+            y[(long) r * ldy + (long) i * HD_LEAF + t] += alpha * v;
+        }
+    }
 }
 
 // r <- b - r (r holds M x), and max |r_i| / max |b_i| per vector into out[2 v], out[2 v + 1]
@@ -565,10 +577,10 @@ int hd_symv_lower(cudaStream_t st, const double *A, long ld, int np, const doubl
         g_hd_launches += ws ? 2 : 1;
         if (nr == 2) {
             symv_lower_kernel<2><<<(unsigned) tiles, 256, 0, st>>>(A, ld, nb, d_x + (long) r0 * ldx, ldx, d_y + (long) r0 * ldy, ldy, alpha, ws);
-            if (ws) symv_reduce_kernel<2><<<nb, HD_LEAF, 0, st>>>(ws, nb, d_y + (long) r0 * ldy, ldy, alpha);
+            if (ws) symv_reduce_kernel<2><<<nb, HD_LEAF * SVR_G, 0, st>>>(ws, nb, d_y + (long) r0 * ldy, ldy, alpha);
         } else {
             symv_lower_kernel<1><<<(unsigned) tiles, 256, 0, st>>>(A, ld, nb, d_x + (long) r0 * ldx, ldx, d_y + (long) r0 * ldy, ldy, alpha, ws);
-            if (ws) symv_reduce_kernel<1><<<nb, HD_LEAF, 0, st>>>(ws, nb, d_y + (long) r0 * ldy, ldy, alpha);
+            if (ws) symv_reduce_kernel<1><<<nb, HD_LEAF * SVR_G, 0, st>>>(ws, nb, d_y + (long) r0 * ldy, ldy, alpha);
         }
     }
     HD_CUDA(cudaGetLastError());
