@@ -105,6 +105,12 @@ __global__ void mail_collect_kernel(const char *ctrl, int P, int self, int seq, 
         out[i] = (r == self) ? val[t] : mail[r * MAIL_CNT + t];
     }
 }
+// LDL^T mode: every rank computed its static-pivoting floor from the diagonal entries it owns; all use the largest
+__global__ void floor_max_kernel(const double *floors, int P, double *floorp) {
+    double v = floors[0];
+    for (int q = 1; q < P; ++q) v = fmax(v, floors[q]);
+    *floorp = v;
+}
 } // namespace
 
 struct DistRank {
@@ -117,6 +123,7 @@ struct DistRank {
     std::vector<cudaEvent_t> ev_full; // ... diagonal block and inverse leaves landed
     char *ctrl = nullptr;
     int *h_ctrl = nullptr;
+    double *d_floors = nullptr;            // [MAXP] pivot floors of all ranks (LDL^T mode)
     struct Peer {
         DistRank *local = nullptr;
         double *L = nullptr, *Dinv = nullptr, *sgn = nullptr;
@@ -280,7 +287,7 @@ void dist_destroy(DistChol *d) {
         cudaEventDestroy(R->ev_col); cudaEventDestroy(R->ev_diag); cudaEventDestroy(R->ev_panel); cudaEventDestroy(R->ev_ready);
         for (auto &e : R->ev_recv) cudaEventDestroy(e);
         for (auto &e : R->ev_full) cudaEventDestroy(e);
-        cudaFree(R->ctrl); cudaFreeHost(R->h_ctrl);
+        cudaFree(R->ctrl); cudaFreeHost(R->h_ctrl); if (R->d_floors) cudaFree(R->d_floors);
         delete R;
     }
     delete d;
@@ -323,7 +330,39 @@ int dist_connect(DistChol *d, const void *blobs) {
 
 // Factor.  On entry the block columns owned by each local rank hold M (lower part, rows >= the block's first row,
 // identity padded); on exit every local rank's buffer holds the complete factor and all inverse leaves.
-// ldl: unpivoted L J L^T (signed Cholesky, chol.cu) instead of Cholesky; the sign vector travels with the panels
+int dist_allgather_small(DistChol *d, const double *d_val, int cnt, double *d_out);
+
+// One static-pivoting floor for the whole matrix: the maximum of the per-rank floors (each from the owned diagonal entries).
+static int dist_common_floor(DistChol *d) {
+    const int P = d->P;
+    if (P <= 1) return HD_OK;
+    if (d->nlocal == P) { // all ranks in this process (self-test): through the host
+        double mx = 0.0;
+        for (int i = 0; i < P; ++i) {
+            DistRank *R = d->local[i];
+            double v = 0.0;
+            HD_CUDA(cudaSetDevice(R->dev));
+            HD_CUDA(cudaStreamSynchronize(R->st));
+            HD_CUDA(cudaMemcpy(&v, R->chol->dfloor, sizeof(double), cudaMemcpyDeviceToHost));
+            mx = v > mx ? v : mx;
+        }
+        for (int i = 0; i < P; ++i) {
+            DistRank *R = d->local[i];
+            HD_CUDA(cudaSetDevice(R->dev));
+            HD_CUDA(cudaMemcpy(R->chol->dfloor, &mx, sizeof(double), cudaMemcpyHostToDevice));
+        }
+        return HD_OK;
+    }
+    if (d->nlocal != 1) return HD_FAILED;
+    DistRank *R = d->local[0];
+    if (!R->d_floors) HD_CUDA(cudaMalloc(&R->d_floors, sizeof(double) * MAXP));
+    HD_CALL(dist_allgather_small(d, R->chol->dfloor, 1, R->d_floors));
+    HDK(floor_max_kernel)<<<1, 1, 0, R->st>>>(R->d_floors, P, R->chol->dfloor);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+// ldl: L J L^T (signed Cholesky with Bunch-Kaufman leaves, chol.cu) instead of Cholesky; the sign vector travels with the panels
 int dist_factor(DistChol *d, int *info_out, bool ldl) {
     if (!d->connected) return HD_FAILED;
     d->epoch++;
@@ -335,6 +374,11 @@ int dist_factor(DistChol *d, int *info_out, bool ldl) {
         HD_CUDA(cudaMemsetAsync(R->chol->dinfo, 0, sizeof(int), R->st));
         R->chol->ldl = ldl;
         if (ldl) HD_CALL(chol_ldl_prepare(R->st, R->chol, nb, R->rank, P));
+    }
+    if (ldl) HD_CALL(dist_common_floor(d)); // before the events below: the side streams order themselves after them
+    for (int i = 0; i < d->nlocal; ++i) {
+        DistRank *R = d->local[i];
+        HD_CUDA(cudaSetDevice(R->dev));
         HD_CUDA(cudaEventRecord(R->ev_ready, R->st));
         HD_CUDA(cudaEventRecord(R->ev_diag, R->st));
         HD_CUDA(cudaEventRecord(R->ev_col, R->st));
