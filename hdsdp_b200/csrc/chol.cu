@@ -636,6 +636,27 @@ int potrf_rec(cudaStream_t st, double *A, long lda, int n, double *dinv, int *in
 
 // X (n x n upper triangular, ld ldx) = L^-T.   Block formula:
 //   X11 = L11^-T, X22 = L22^-T, X12 = -(X11 L21^T) L22^-T  (the right factor applied by trsm_rec)
+// The two diagonal sub-blocks of the recursion are independent.  Below INV_FORK_N their products are a handful of CTAs each
+// (latency-bound), so the second one is enqueued on another stream of a small pool and joined before the off-diagonal
+// block: up to 8 branches of the tree run side by side (forks nest).  Events are reused round-robin: a wait captures the
+// event's state when it is enqueued, and every record is followed by its wait before the event comes round again (a node
+// of 2048 has ~30 events pending at most).
+constexpr int INV_POOL = 8, INV_EVENTS = 256;
+int g_inv_fork_n = 2048; // "invert_fork": largest node that forks (0 = off)
+cudaStream_t g_inv_pool[INV_POOL] = {nullptr};
+cudaEvent_t g_inv_ev[INV_EVENTS] = {nullptr};
+int g_inv_next_stream = 0, g_inv_next_event = 0;
+cudaEvent_t inv_event() {
+    cudaEvent_t &e = g_inv_ev[g_inv_next_event++ % INV_EVENTS];
+    if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+cudaStream_t inv_stream() {
+    cudaStream_t &s = g_inv_pool[g_inv_next_stream++ % INV_POOL];
+    if (!s) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    return s;
+}
+
 int invert_rec(cudaStream_t st, const double *L, long ldl, int n, const double *dinv, double *X, long ldx) {
     if (n == HD_LEAF) {
         HDK(leaf_transpose_kernel)<<<dim3(4, 4), dim3(32, 8), 0, st>>>(dinv, X, ldx);
@@ -644,14 +665,28 @@ int invert_rec(cudaStream_t st, const double *L, long ldl, int n, const double *
     }
     int n1 = split_leaves(n), n2 = n - n1;
     const double *dinv2 = dinv + (long) (n1 / HD_LEAF) * HD_LEAF * HD_LEAF;
-    HD_CALL(invert_rec(st, L, ldl, n1, dinv, X, ldx));
-    HD_CALL(invert_rec(st, L + (long) n1 * ldl + n1, ldl, n2, dinv2, X + (long) n1 * ldx + n1, ldx));
+    cudaEvent_t joined = nullptr;
+    if (n <= g_inv_fork_n && n2 >= 2 * HD_LEAF) {
+        cudaStream_t s2 = inv_stream();
+        cudaEvent_t fork = inv_event(), done = inv_event();
+        HD_CUDA(cudaEventRecord(fork, st));
+        HD_CUDA(cudaStreamWaitEvent(s2, fork, 0));
+        HD_CALL(invert_rec(s2, L + (long) n1 * ldl + n1, ldl, n2, dinv2, X + (long) n1 * ldx + n1, ldx));
+        HD_CUDA(cudaEventRecord(done, s2));
+        HD_CALL(invert_rec(st, L, ldl, n1, dinv, X, ldx));
+        joined = done; // X22 is not read by the two products below (they use L22 and its inverse leaves): join after them
+    } else {
+        HD_CALL(invert_rec(st, L, ldl, n1, dinv, X, ldx));
+        HD_CALL(invert_rec(st, L + (long) n1 * ldl + n1, ldl, n2, dinv2, X + (long) n1 * ldx + n1, ldx));
+    }
     GemmArgs g{};
     g.M = n1; g.N = n2; g.K = n1;
     g.A = X; g.lda = ldx; g.B = L + n1; g.ldb = ldl; g.C = X + (long) n1 * ldx; g.ldc = ldx;
     g.alpha = -1.0; g.beta = 0.0; g.flags = n1 >= 1024 ? HD_GEMM_KTRI_A : 0; // X11 is upper triangular: half the k-range on average
     HD_CALL(hd_gemm_nt(st, g));
-    return trsm_rec(st, X + (long) n1 * ldx, ldx, n1, L + (long) n1 * ldl + n1, ldl, n2, dinv2);
+    HD_CALL(trsm_rec(st, X + (long) n1 * ldx, ldx, n1, L + (long) n1 * ldl + n1, ldl, n2, dinv2));
+    if (joined) HD_CUDA(cudaStreamWaitEvent(st, joined, 0));
+    return HD_OK;
 }
 
 } // namespace
@@ -760,6 +795,7 @@ static int g_lookahead_nb = -1; // block size; 0 disables the blocked path; -1 =
 void hd_chol_set_block(int nb) { g_lookahead_nb = nb; }
 void hd_chol_set_leaf(int v) { g_leaf_version = v; }
 void hd_chol_set_ldl_pivot(int v) { g_ldl_pivot = v != 0; }
+void hd_chol_set_invert_fork(int v) { g_inv_fork_n = v; }
 int hd_leaf_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_leaf_clk, sizeof(long long) * 40) == cudaSuccess ? HD_OK : HD_FAILED; }
 
 static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {

@@ -56,6 +56,7 @@ int hdsdpcu_debug_leafclk(long long *out);
  *                  leaf; 0 = unpivoted L J L^T with static pivoting only (round-1 behaviour)
  *   "chol_partition" strip schedule: 1 = the chain runs in an 8-SM green-context partition, the bulk GEMMs in the other 140 SMs;
  *                  0 (default) = both share all SMs (stream priorities only).  Measured slower on B200
+ *   "invert_fork"  S^-1: sub-blocks of the recursion for L^-T up to this size run on a pool of streams (default 2048, 0 = one stream)
  *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default)
  *   "chol_graph"   1 (default): factorisations up to n = 6144 are replayed from a captured CUDA graph from their third call on */
 int hdsdpcu_set_option(const char *name, int value);
