@@ -64,6 +64,7 @@ int hdsdpcu_init(int device) {
         if (const char *e = getenv("HDSDPCU_CHOL_GRAPH")) hd_chol_set_graph(atoi(e));
         if (const char *e = getenv("HDSDPCU_DIST_DELAY")) hd_dist_set_delay(atoi(e));
         if (const char *e = getenv("HDSDPCU_INVERT_FORK")) hd_chol_set_invert_fork(atoi(e));
+        if (const char *e = getenv("HDSDPCU_CHOL_TAIL")) hd_chol_set_tail(atoi(e));
     }
     g_ready = true;
     return HD_OK;
@@ -110,6 +111,7 @@ int hdsdpcu_set_option(const char *name, int value) {
     if (name && strcmp(name, "chol_leaf") == 0) { hd_chol_set_leaf(value); return HD_OK; }
     if (name && strcmp(name, "ldl_pivot") == 0) { hd_chol_set_ldl_pivot(value); return HD_OK; }
     if (name && strcmp(name, "invert_fork") == 0) { hd_chol_set_invert_fork(value); return HD_OK; }
+    if (name && strcmp(name, "chol_tail") == 0) { hd_chol_set_tail(value); return HD_OK; }
     if (name && strcmp(name, "chol_partition") == 0) { hd_chol_set_partition(value); return HD_OK; }
     if (name && strcmp(name, "trsv_version") == 0) { hd_trsv_set_version(value); return HD_OK; }
     if (name && strcmp(name, "chol_graph") == 0) { hd_chol_set_graph(value); return HD_OK; }

@@ -798,7 +798,24 @@ void hd_chol_set_ldl_pivot(int v) { g_ldl_pivot = v != 0; }
 void hd_chol_set_invert_fork(int v) { g_inv_fork_n = v; }
 int hd_leaf_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_leaf_clk, sizeof(long long) * 40) == cudaSuccess ? HD_OK : HD_FAILED; }
 
-static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
+static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB, int base0);
+static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB, int base0, bool tails);
+static int auto_block(int np) { return np <= 7168 ? 128 : (np < 14336 ? 256 : (np < 24000 ? 512 : (np < 40000 ? 1024 : 2048))); }
+static int g_tail = 1; // "chol_tail": hand the trailing matrix over to the schedule of its own size (see potrf_blocked)
+static int g_tail_pct = 100; // probe knob: values > 1 scale the hand-over thresholds (percent)
+void hd_chol_set_tail(int v) { g_tail = v != 0; g_tail_pct = v > 1 ? v : 100; }
+
+// Factor a trailing sub-matrix (fully updated, nothing of it factored yet) with the block size and schedule a matrix of that size
+// would get on its own.
+static int potrf_tail(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int base0) {
+    const int nb = auto_block(np);
+    const int sched = g_sched > 0 ? g_sched : (np <= 10240 ? 3 : 1);
+    if (np >= 4 * nb && !g_ldl && sched >= 2) return potrf_blocked2(st, A, lda, np, dinv, info, nb, base0);
+    if (np >= 4 * nb) return potrf_blocked(st, A, lda, np, dinv, info, nb, base0, true);
+    return potrf_rec(st, A, lda, np, dinv, info, base0);
+}
+
+static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB, int base0, bool tails) {
     if (!g_side) {
         int lo = 0, hi = 0;
         HD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -814,7 +831,7 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
     auto size = [&](int k) { return (k == nblk - 1) ? np - k * NB : NB; };
     auto leaves = [&](int k) { return dinv + (long) (start(k) / HD_LEAF) * HD_LEAF * HD_LEAF; };
     // panel 0 on the main stream
-    HD_CALL(potrf_rec(st, A, lda, size(0), leaves(0), info, 0));
+    HD_CALL(potrf_rec(st, A, lda, size(0), leaves(0), info, base0));
     mark();
     if (nblk > 1) HD_CALL(trsm_rec(st, A + size(0), lda, np - size(0), A, lda, size(0), leaves(0)));
     mark();
@@ -827,6 +844,21 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
     for (int k = 0; k + 1 < nblk; ++k) {
         const int s0 = start(k), b0 = size(k), s1 = start(k + 1), b1 = size(k + 1);
         const double *P = A + s0 * lda; // panel k: rows s1.. are the solved block column
+        // Tail hand-over.  Late in the factorisation the panel chain (leaves and thin products of a NB-wide diagonal block, each
+        // waiting for a CTA slot behind trailing-update CTAs that run for NB / 7 us) outlasts the trailing update: at m = 50 000,
+        // NB = 2048 the main stream waited 2.5 ms per step over the last nine steps (HDSDPCU_TRACE).  Once the rest is small
+        // enough, panel k is applied to ALL of it and the rest is factored with the block size / schedule of its own size.
+        // Measured (tools/trace_potrf.py, hand-over off / on): n = 50 000 1297.8 / 1290.6 ms, 30 000 297.3 / 294.7, 20 000 95.2 / 93.8.
+        const int rem = np - s1;
+        const int tail_n = (int) ((long) (NB >= 2048 ? 12288 : (NB >= 1024 ? 8704 : (NB >= 512 ? 5632 : (NB >= 256 ? 3584 : 0)))) * g_tail_pct / 100);
+        if (tails && !trace && rem <= tail_n && rem >= 8 * HD_LEAF) {
+            GemmArgs g{};
+            g.M = rem; g.N = rem; g.K = b0;
+            g.A = P + s1; g.lda = lda; g.B = P + s1; g.ldb = lda; g.C = A + (long) s1 * lda + s1; g.ldc = lda;
+            g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER; g.ksign = sgn_of(leaves(k));
+            HD_CALL(hd_gemm_nt(st, g));
+            return potrf_tail(st, A + (long) s1 * lda + s1, lda, rem, leaves(k + 1), info, base0 + s1);
+        }
         cudaStream_t cst = col_on_side ? g_side : st;
         if (col_on_side) HD_CUDA(cudaStreamWaitEvent(g_side, g_ev_trail, 0)); // trailing update k-1 (and panel 0) done
         // (1) update block column k+1: diagonal block (lower tiles) and the rectangle below it
@@ -847,7 +879,7 @@ static int potrf_blocked(cudaStream_t st, double *A, long lda, int np, double *d
         }
         mark();
         // (2) side stream: factor block k+1 and solve its panel
-        HD_CALL(potrf_rec(g_side, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1), info, s1));
+        HD_CALL(potrf_rec(g_side, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1), info, base0 + s1));
         if (below > 0) HD_CALL(trsm_rec(g_side, A + (long) s1 * lda + s1 + b1, lda, below, A + (long) s1 * lda + s1, lda, b1, leaves(k + 1)));
         HD_CUDA(cudaEventRecord(g_ev_panel, g_side));
         // (3) main stream: the rest of the trailing matrix (columns of blocks k+2..)
@@ -969,7 +1001,7 @@ int hd_chol_partition_sms(int *chain, int *bulk) {
 }
 static cudaEvent_t g_ev_fork = nullptr;
 
-static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB) {
+static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *dinv, int *info, int NB, int base0) {
     if (!g_side) {
         int lo = 0, hi = 0;
         HD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1012,7 +1044,7 @@ static int potrf_blocked2(cudaStream_t st, double *A, long lda, int np, double *
             g.alpha = -1.0; g.beta = 1.0; g.flags = HD_GEMM_LOWER;
             HD_CALL(hd_gemm_nt(side, g));                                                  // DIAGUPD(k)
         }
-        HD_CALL(potrf_rec(side, at(s0, s0), lda, b0, leaves(k), info, s0));                // POTRF(k)
+        HD_CALL(potrf_rec(side, at(s0, s0), lda, b0, leaves(k), info, base0 + s0));        // POTRF(k)
         HD_CUDA(cudaEventRecord(g_evs[0][k], side));
         if (b1 > 0) {
             if (k >= 1) HD_CUDA(cudaStreamWaitEvent(side, g_evs[2][k - 1], 0));          // UPDCOL(k-1): column block k below its diagonal
@@ -1122,9 +1154,9 @@ static int enqueue_factor(cudaStream_t st, DenseChol *c, int nb) {
     int rc;
     const int sched = g_sched > 0 ? g_sched : (c->np <= 10240 ? 3 : 1);
     if (nb >= HD_LEAF && c->np >= 4 * nb && !c->ldl && sched >= 2)
-        rc = potrf_blocked2(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF);
+        rc = potrf_blocked2(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF, 0);
     else if (nb >= HD_LEAF && c->np >= 4 * nb)
-        rc = potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF);
+        rc = potrf_blocked(st, c->L, c->np, c->np, c->Dinv, c->dinfo, (nb / HD_LEAF) * HD_LEAF, 0, g_tail && g_lookahead_nb < 0);
     else
         rc = potrf_rec(st, c->L, c->np, c->np, c->Dinv, c->dinfo, 0);
     g_ldl = nullptr;
@@ -1139,7 +1171,7 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     HD_CALL(ensure_leaf_attr());
     int nb = g_lookahead_nb;
     // measured (tools/trace_potrf.py, B200): strip schedule with NB = 128 up to 7k, 256 up to 10k; one-step look-ahead beyond
-    if (nb < 0) nb = c->np <= 7168 ? 128 : (c->np < 14336 ? 256 : (c->np < 24000 ? 512 : (c->np < 40000 ? 1024 : 2048)));
+    if (nb < 0) nb = auto_block(c->np);
     // Up to n = 6k the factorisation is a launch-bound chain of a few hundred small kernels on two streams whose shapes
     // depend only on (n, block, mode): the second call with the same configuration captures it into a CUDA graph, later
     // calls replay the graph (one launch, dependencies resolved on the device).  The first call runs eagerly so that
@@ -1147,7 +1179,7 @@ int chol_factor(cudaStream_t st, DenseChol *c, int *info) {
     // -3 % at 4096, +2 % at 8192 and beyond (stream priorities are not honoured inside a graph), hence the size limit.
     const unsigned long long key = 1ull | ((unsigned long long) nb << 8) | ((unsigned long long) (c->ldl ? 1 : 0) << 1) |
                                    ((unsigned long long) g_leaf_version << 2) | ((unsigned long long) hd_gemm_get_variant() << 4) |
-                                   ((unsigned long long) (g_sched + 1) << 40) | ((unsigned long long) g_ldl_pivot << 44) | ((unsigned long long) (g_partition > 0) << 45);
+                                   ((unsigned long long) (g_sched + 1) << 40) | ((unsigned long long) g_ldl_pivot << 44) | ((unsigned long long) (g_partition > 0) << 45) | ((unsigned long long) g_tail << 46);
     const bool graph_ok = g_use_graph && c->np <= g_graph_max && getenv("HDSDPCU_TRACE") == nullptr;
     if (graph_ok && c->graph_exec && c->graph_key == key) {
         HD_CUDA(cudaGraphLaunch((cudaGraphExec_t) c->graph_exec, st));

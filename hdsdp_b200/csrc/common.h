@@ -97,6 +97,7 @@ void hd_dist_set_delay(int on);
 void hd_chol_set_leaf(int v);
 void hd_chol_set_ldl_pivot(int v);
 void hd_chol_set_invert_fork(int v);
+void hd_chol_set_tail(int v);
 void hd_chol_set_partition(int v);
 int hd_chol_partition_sms(int *chain, int *bulk);
 void hd_trsv_set_version(int v);

@@ -57,6 +57,8 @@ int hdsdpcu_debug_leafclk(long long *out);
  *   "chol_partition" strip schedule: 1 = the chain runs in an 8-SM green-context partition, the bulk GEMMs in the other 140 SMs;
  *                  0 (default) = both share all SMs (stream priorities only).  Measured slower on B200
  *   "invert_fork"  S^-1: sub-blocks of the recursion for L^-T up to this size run on a pool of streams (default 2048, 0 = one stream)
+ *   "chol_tail"    1 (default): late in a large factorisation the trailing matrix is handed over to the block size / schedule of
+ *                  its own size (2048 -> 512 -> 256 -> strip chain); 0 = one block size throughout (also HDSDPCU_CHOL_TAIL)
  *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default)
  *   "chol_graph"   1 (default): factorisations up to n = 6144 are replayed from a captured CUDA graph from their third call on */
 int hdsdpcu_set_option(const char *name, int value);
