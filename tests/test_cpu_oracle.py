@@ -131,3 +131,31 @@ def test_oracle_potrf_detects_indefinite():
     A[1, 1] = 1.0
     assert l.orc_potrf(3, oracle._dp(A), oracle._dp(L)) == 0
     np.testing.assert_allclose(np.tril(L), np.linalg.cholesky(np.tril(A) + np.tril(A, -1).T), rtol=1e-14)
+
+
+def test_recorded_reference_end_points_match_a_live_reference_run():
+    """tests/golden/ref_endpoints.json (tests/golden/make_endpoints.py) holds the full-solve end points the unmodified reference
+    reaches with 1 / 2 / 4 / 8 BLAS threads; the GPU full-solve test accepts any of them.  Where the reference build is
+    present, a live single-thread run of the small LP-cone problem must land on a recorded end point (dObj 1e-7, same count)."""
+    import json
+    import os
+    import sys
+    from conftest import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "ref_endpoints.json")) as f:
+        rec = json.load(f)
+    assert set(rec) == {"theta:200:3000", "maxcut:1000:4", "maxcutlp:300:4"}
+    for spec, runs in rec.items():
+        assert [r["threads"] for r in runs] == [1, 2, 4, 8] and all(r["status"] == runs[0]["status"] for r in runs)
+    # the two branches of theta n = 200 are both on record
+    its = sorted({r["iterations"] for r in rec["theta:200:3000"]})
+    assert its[0] <= 34 and its[-1] >= 47, its
+    from oracle import refdrv
+    if not refdrv.available():
+        pytest.skip("oracle/_ref not built")
+    sys.path.insert(0, ROOT)
+    from tools import fullsolve
+    s = fullsolve.parse_spec("maxcutlp:300:4")
+    r, log, err = fullsolve.run(s, False, 1)
+    assert r is not None, err[-2000:]
+    near = min(rec["maxcutlp:300:4"], key=lambda c: abs(c["dObj"] - r["dObj"]))
+    assert abs(near["dObj"] - r["dObj"]) <= 1e-7 * abs(near["dObj"]) and abs(near["iterations"] - r["iterations"]) <= 1
