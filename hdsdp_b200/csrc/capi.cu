@@ -64,6 +64,7 @@ int hdsdpcu_init(int device) {
         if (const char *e = getenv("HDSDPCU_CHOL_GRAPH")) hd_chol_set_graph(atoi(e));
         if (const char *e = getenv("HDSDPCU_DIST_DELAY")) hd_dist_set_delay(atoi(e));
         if (const char *e = getenv("HDSDPCU_INVERT_FORK")) hd_chol_set_invert_fork(atoi(e));
+        if (const char *e = getenv("HDSDPCU_TRSV_VERSION")) hd_trsv_set_version(atoi(e));
         if (const char *e = getenv("HDSDPCU_CHOL_TAIL")) hd_chol_set_tail(atoi(e));
     }
     g_ready = true;

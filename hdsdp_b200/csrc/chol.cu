@@ -738,7 +738,7 @@ int chol_create(DenseChol **pc, int n) {
         cudaFree(c->L); free(c); cudaGetLastError(); return HD_MEMORY;
     }
     if (cudaMalloc(&c->DinvT, (size_t) c->np * HD_LEAF * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&c->sync, sizeof(int) * (c->np / HD_LEAF + 2)) != cudaSuccess) {
+        cudaMalloc(&c->sync, sizeof(int) * (2 * (c->np / HD_LEAF) + 4)) != cudaSuccess) {
         cudaFree(c->L); cudaFree(c->Dinv); free(c); cudaGetLastError(); return HD_MEMORY;
     }
     if (cudaMalloc(&c->dinfo, sizeof(int)) != cudaSuccess || cudaMallocHost(&c->hinfo, sizeof(int)) != cudaSuccess) {

@@ -59,7 +59,8 @@ int hdsdpcu_debug_leafclk(long long *out);
  *   "invert_fork"  S^-1: sub-blocks of the recursion for L^-T up to this size run on a pool of streams (default 2048, 0 = one stream)
  *   "chol_tail"    1 (default): late in a large factorisation the trailing matrix is handed over to the block size / schedule of
  *                  its own size (2048 -> 512 -> 256 -> strip chain); 0 = one block size throughout (also HDSDPCU_CHOL_TAIL)
- *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles (default)
+ *   "trsv_version" triangular solves: 1 = streaming, 2 = register-prefetched tiles, one CTA per row block (default),
+ *                  3 = one ticket per 128 x 128 tile with ordered accumulation (measured slower: DESIGN.md section 7)
  *   "chol_graph"   1 (default): factorisations up to n = 6144 are replayed from a captured CUDA graph from their third call on */
 int hdsdpcu_set_option(const char *name, int value);
 

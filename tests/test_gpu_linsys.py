@@ -256,7 +256,7 @@ def test_bunch_kaufman_leaf_agrees_with_static_ldl_where_no_pivoting_is_needed()
     assert np.abs(A @ xs[0] - b).max() <= 1e-12 * np.abs(b).max() * n
 
 
-@pytest.mark.parametrize("leaf,trsv", [(1, 1), (1, 2), (2, 1)])
+@pytest.mark.parametrize("leaf,trsv", [(1, 1), (1, 2), (2, 1), (2, 3)])
 def test_alternative_kernel_versions(leaf, trsv):
     """The measurement knobs (include/hdsdpcu.h hdsdpcu_set_option) select older kernel generations: they must stay correct."""
     from hdsdp_b200 import _lib
@@ -276,3 +276,37 @@ def test_alternative_kernel_versions(leaf, trsv):
         ls.close()
     finally:
         lib.hdsdpcu_set_option(b"chol_leaf", 2); lib.hdsdpcu_set_option(b"trsv_version", 2)
+
+
+@pytest.mark.parametrize("n", [130, 1000, 3001])
+def test_tile_ticket_triangular_solves(n):
+    """trsv_version 3 (one work item per 128 x 128 tile, ordered accumulation): forward, backward and full solves for 1 .. 5
+    right-hand sides against the default kernels (1e-12) and against numpy; twice, to see the run-to-run determinism of the
+    ordered sums."""
+    from hdsdp_b200 import _lib
+    from hdsdp_b200.api import DenseLinsys
+    lib = _lib.require_gpu()
+    A = spd(n, 3 * n)
+    A = np.asfortranarray(0.5 * (A + A.T))
+    Lref = np.linalg.cholesky(A)
+    ls = DenseLinsys(n)
+    assert ls.numeric(A) == 0
+    rs = np.random.RandomState(n)
+    try:
+        for nrhs in (1, 2, 3, 5):
+            B = rs.standard_normal((n, nrhs)) if nrhs > 1 else rs.standard_normal(n)
+            out = {}
+            for ver in (2, 3, 3):
+                assert lib.hdsdpcu_set_option(b"trsv_version", ver) == 0
+                out.setdefault(ver, []).append((ls.fsolve(B), ls.bsolve(B), ls.solve(B)))
+            (f2, b2, s2), (f3, b3, s3), (f3b, b3b, s3b) = out[2][0], out[3][0], out[3][1]
+            for got, ref in ((f3, f2), (b3, b2), (s3, s2)):
+                assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+            assert np.array_equal(f3, f3b) and np.array_equal(b3, b3b) and np.array_equal(s3, s3b)
+            Bm = B.reshape(n, -1)
+            assert np.abs(Lref @ f3.reshape(n, -1) - Bm).max() <= 1e-11 * np.abs(Bm).max() * n
+            assert np.abs(Lref.T @ b3.reshape(n, -1) - Bm).max() <= 1e-11 * np.abs(Bm).max() * n
+            assert np.abs(A @ s3.reshape(n, -1) - Bm).max() <= 1e-10 * np.abs(Bm).max() * n
+    finally:
+        lib.hdsdpcu_set_option(b"trsv_version", 2)
+        ls.close()
