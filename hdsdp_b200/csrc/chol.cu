@@ -391,7 +391,8 @@ potf2_leaf2_kernel(double *A, long lda, double *Dinv, int *info, int base, doubl
 // kernel writes Dinv = |Lambda|^(-1/2) Q^T L^-1 P^T, the signs and (for checks only) G into the full leaf.  |lambda| <= *floorp
 // is replaced by +floorp and counted (static pivoting stays as the backstop for a leaf that is singular as a whole: pivots
 // are never taken from another leaf, so this is weaker than dsytrf -- the residual gate of the KKT solve covers the rest).
-// One CTA, the full symmetric leaf in shared memory; a fallback path, written for clarity: ~0.2 ms per leaf.
+// One CTA, the full symmetric leaf in shared memory; a fallback path, written for clarity: 0.35 ms per leaf against 45 us for
+// the Cholesky leaf (tools/probe_ldl.py: LDL^T of n = 8192 32.8 ms, unpivoted 11.7 ms; n = 20 000 127 ms vs 101 ms).
 constexpr int BK_LD = HD_LEAF + 1, BK_THREADS = 256;
 constexpr int BK_SMEM = (HD_LEAF * BK_LD + 4 * HD_LEAF) * 8;
 
